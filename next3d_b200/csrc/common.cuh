@@ -1,0 +1,44 @@
+// Shared helpers for libnext3d_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+// Error codes returned by every extern "C" entry point (include/next3d_b200.h).
+#define N3D_OK 0
+#define N3D_ERR_INVALID_ARG (-1)
+#define N3D_ERR_UNSUPPORTED (-2)
+#define N3D_ERR_CUDA (-3)
+
+void n3d_set_error(const char* fmt, ...);
+
+#define N3D_CHECK_ARG(cond, ...)                        \
+    do {                                                \
+        if (!(cond)) {                                  \
+            n3d_set_error(__VA_ARGS__);                 \
+            return N3D_ERR_INVALID_ARG;                 \
+        }                                               \
+    } while (0)
+
+#define N3D_CHECK_LAUNCH(name)                                                       \
+    do {                                                                             \
+        cudaError_t e__ = cudaGetLastError();                                        \
+        if (e__ != cudaSuccess) {                                                    \
+            n3d_set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));   \
+            return N3D_ERR_CUDA;                                                     \
+        }                                                                            \
+    } while (0)
+
+static inline int n3d_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// fp32 -> (hi, lo) bf16 pair with hi + lo ~= x to ~16 mantissa bits (used by the 3-product tensor-core scheme).
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(x);
+    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
+    return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}

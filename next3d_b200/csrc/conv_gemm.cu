@@ -1,0 +1,443 @@
+// Implicit-GEMM convolution on tcgen05 tensor cores (sm_100a) -- the dense contraction of every conv layer of the
+// generator (modulated 3x3 / 1x1, transposed-conv parity classes, stride-2 convs, ToRGB).
+//
+//   M = 128 output pixels per tile (TN x TH x TW patch), N = block_n output channels, K = taps x Cin.
+//   A (activations, NHWC bf16, split hi/lo) is fetched per (tap, 64-channel chunk) as one 4-D TMA box whose
+//   coordinates are shifted by the tap offset; out-of-range rows/columns are zero-filled by TMA, which *is* the
+//   convolution padding.  B (weights [T, Cout, Cin] bf16 hi/lo) is a 3-D TMA box.  Both land in shared memory in the
+//   K-major SWIZZLE_128B layout that tcgen05.mma consumes directly.
+//   Precision: fp32 = hi + lo with bf16 hi, lo; acc += Ahi*Bhi + Ahi*Blo + Alo*Bhi (3 MMAs, fp32 accumulate in TMEM)
+//   reproduces an fp32 convolution to ~2^-16 relative -- inside the 1e-3 end-to-end budget where single-pass
+//   bf16/fp16/tf32 is not (SURVEY.md section 7 "Precision vs tensor cores").
+//   Warp roles (256 threads, persistent over tiles): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
+//   warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> fused demod/noise/bias/lrelu/clamp ->
+//   next layer's modulation -> bf16 split / fp32 stores).  Two TMEM accumulator buffers overlap the epilogue of
+//   tile i with the MMAs of tile i+1.
+#include "common.cuh"
+#include "../../include/next3d_b200.h"
+#include <cuda.h>
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                    // bf16 elements = 128 bytes = one swizzle row
+constexpr int kABytes = kBlockM * kBlockK * 2; // 16 KiB per A tile
+constexpr int kThreads = 256;
+constexpr uint32_t kSpinLimit = 1u << 24;
+
+struct KParams {
+    CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
+    int N, MH, MW, Cout;
+    int TW, TH, TN;                  // TW*TH*TN == 128, all powers of two
+    int tiles_x, tiles_y, tiles_i, tiles_n;
+    int block_n, acc_stride, tmem_cols, stages, stage_bytes, b_bytes;
+    int cin_chunks, ntaps, nprod, a_img_stride;
+    N3DConvTap taps[9];
+    int mode;
+    const float* dcoef; const float* bias; const float* noise;
+    float gain, slope, clamp;
+    N3DSplitOut out[2];
+    float* out_f32; int f32_cstride, f32_coff, f32_nchw, f32_accumulate;
+    int oy_mul, oy_off, ox_mul, ox_off, OH, OW;
+    int* err_flag;
+};
+
+// ---------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug traps (kernel aborts with an error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err_flag, int code) {
+#pragma unroll 1
+    for (uint32_t it = 0; it < kSpinLimit; ++it)
+        if (mbar_try_wait(bar, parity)) return;
+    if (err_flag) atomicExch(err_flag, code);
+    __trap();
+}
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46) = 1024 B between 8-row groups, version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------- the kernel
+__global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ KParams P) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // dynamic smem base is only guaranteed 16-B aligned: round up to 1024 (SWIZZLE_128B atoms)
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + (uint32_t)P.stages * (uint32_t)P.stage_bytes;   // 8-byte aligned
+    // barriers: full[stages], empty[stages], tmem_full[2], tmem_empty[2]; then the TMEM base address word
+    auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(P.stages + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (uint32_t)(2 * P.stages + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (uint32_t)(2 * P.stages + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(2 * P.stages + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&P.tmA_hi); tma_prefetch_desc(&P.tmB_hi);
+        if (P.nprod == 3) { tma_prefetch_desc(&P.tmA_lo); tma_prefetch_desc(&P.tmB_lo); }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < P.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)P.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    const int tiles_m = P.tiles_x * P.tiles_y * P.tiles_i;
+    const int total_tiles = tiles_m * P.tiles_n;
+    const int ksteps = P.ntaps * P.cin_chunks;
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            const uint32_t tx_bytes = (uint32_t)(P.nprod == 3 ? 2 : 1) * (uint32_t)(kABytes + P.b_bytes);
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int tn = tile % P.tiles_n, tm = tile / P.tiles_n;
+                const int x0 = (tm % P.tiles_x) * P.TW, y0 = ((tm / P.tiles_x) % P.tiles_y) * P.TH;
+                const int n0 = (tm / (P.tiles_x * P.tiles_y)) * P.TN;
+                for (int t = 0; t < P.ntaps; ++t) {
+                    const N3DConvTap tap = P.taps[t];
+                    for (int kc = 0; kc < P.cin_chunks; ++kc) {
+                        mbar_wait(empty_bar(s), ph ^ 1u, P.err_flag, 1);
+                        const uint32_t sa = smem_base + (uint32_t)s * (uint32_t)P.stage_bytes;
+                        const uint32_t fb = full_bar(s);
+                        mbar_expect_tx(fb, tx_bytes);
+                        const int img = n0 + (int)tap.img_off * P.a_img_stride;
+                        tma_load_4d(sa, &P.tmA_hi, fb, kc * kBlockK, x0 + tap.dx, y0 + tap.dy, img);
+                        tma_load_3d(sa + 2 * kABytes, &P.tmB_hi, fb, kc * kBlockK, tn * P.block_n, tap.wtap);
+                        if (P.nprod == 3) {
+                            tma_load_4d(sa + kABytes, &P.tmA_lo, fb, kc * kBlockK, x0 + tap.dx, y0 + tap.dy, img);
+                            tma_load_3d(sa + 2 * kABytes + P.b_bytes, &P.tmB_lo, fb, kc * kBlockK, tn * P.block_n, tap.wtap);
+                        }
+                        if (++s == P.stages) { s = 0; ph ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer
+        if (lane == 0) {
+            // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
+            // both K-major, N>>3 at [17,23), M>>4 at [24,29)
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.block_n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+            int s = 0; uint32_t ph = 0; int acc = 0; uint32_t acc_ph = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(tempty_bar(acc), acc_ph ^ 1u, P.err_flag, 2);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P.acc_stride);
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    mbar_wait(full_bar(s), ph, P.err_flag, 3);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + (uint32_t)s * (uint32_t)P.stage_bytes;
+                    const uint32_t a_hi = sa, a_lo = sa + kABytes, b_hi = sa + 2 * kABytes, b_lo = b_hi + (uint32_t)P.b_bytes;
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        const uint32_t koff = (uint32_t)k * 32u;     // 16 bf16 = 32 bytes inside the 128-B swizzle row
+                        umma_bf16(d_tmem, umma_desc(a_hi + koff), umma_desc(b_hi + koff), idesc, (ks | k) != 0);
+                        if (P.nprod == 3) {
+                            umma_bf16(d_tmem, umma_desc(a_hi + koff), umma_desc(b_lo + koff), idesc, 1u);
+                            umma_bf16(d_tmem, umma_desc(a_lo + koff), umma_desc(b_hi + koff), idesc, 1u);
+                        }
+                    }
+                    umma_commit(empty_bar(s));                 // frees the smem stage once these MMAs retire
+                    if (++s == P.stages) { s = 0; ph ^= 1u; }
+                }
+                umma_commit(tfull_bar(acc));                   // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================================================== epilogue (4 warps = 128 TMEM lanes)
+        const int q = warp & 3;                                // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;                         // tile row = TMEM lane
+        const int tw = row % P.TW, th = (row / P.TW) % P.TH, tnn = row / (P.TW * P.TH);
+        int acc = 0; uint32_t acc_ph = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int tn = tile % P.tiles_n, tm = tile / P.tiles_n;
+            const int x = (tm % P.tiles_x) * P.TW + tw, y = ((tm / P.tiles_x) % P.tiles_y) * P.TH + th;
+            const int n = (tm / (P.tiles_x * P.tiles_y)) * P.TN + tnn;
+            const int oy = y * P.oy_mul + P.oy_off, ox = x * P.ox_mul + P.ox_off;
+            const bool valid = (n < P.N) && (y < P.MH) && (x < P.MW) && (oy < P.OH) && (ox < P.OW);
+            const int64_t opix = ((int64_t)n * P.OH + oy) * P.OW + ox;
+            float nz = 0.f;
+            if (valid && P.noise) nz = __ldg(P.noise + (int64_t)oy * P.OW + ox);
+
+            mbar_wait(tfull_bar(acc), acc_ph, P.err_flag, 4);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * P.acc_stride);
+            for (int c16 = 0; c16 < P.block_n; c16 += 16) {
+                uint32_t r[16];
+                __syncwarp();                                  // tcgen05.ld is warp-collective (.sync.aligned)
+                tmem_ld16(t_row + (uint32_t)c16, r);
+                const int co0 = tn * P.block_n + c16;
+                if (!valid || co0 >= P.Cout) continue;
+                const int nco = min(16, P.Cout - co0);
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float a = __uint_as_float(r[j]);
+                    if (P.mode == 0 && j < nco) {
+                        const int co = co0 + j;
+                        if (P.dcoef) a *= __ldg(P.dcoef + (int64_t)n * P.Cout + co);
+                        a += nz;
+                        if (P.bias) a += __ldg(P.bias + co);
+                        a = (a > 0.f ? a : a * P.slope) * P.gain;
+                        if (P.clamp >= 0.f) a = fminf(fmaxf(a, -P.clamp), P.clamp);
+                    }
+                    v[j] = a;
+                }
+                // ---- fp32 output
+                if (P.out_f32) {
+                    if (P.f32_nchw) {
+                        for (int j = 0; j < nco; ++j) {
+                            float* dst = P.out_f32 + (((int64_t)n * P.f32_cstride + P.f32_coff + co0 + j) * P.OH + oy) * P.OW + ox;
+                            *dst = P.f32_accumulate ? (*dst + v[j]) : v[j];
+                        }
+                    } else {
+                        float* dst = P.out_f32 + opix * P.f32_cstride + P.f32_coff + co0;
+                        if (nco == 16 && !P.f32_accumulate && (((P.f32_cstride | (P.f32_coff + co0)) & 3) == 0)) {
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        } else {
+                            for (int j = 0; j < nco; ++j) dst[j] = P.f32_accumulate ? (dst[j] + v[j]) : v[j];
+                        }
+                    }
+                }
+                // ---- split bf16 outputs (next layers' pre-modulated operands)
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const N3DSplitOut o = P.out[k];
+                    if (!o.hi) continue;
+                    __nv_bfloat16 h[16], l[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float s = v[j];
+                        if (o.style && j < nco) s *= __ldg(o.style + (int64_t)n * P.Cout + co0 + j);
+                        split_bf16(s, h[j], l[j]);
+                    }
+                    __nv_bfloat16* dh = (__nv_bfloat16*)o.hi + opix * o.cstride + o.coff + co0;
+                    __nv_bfloat16* dl = (__nv_bfloat16*)o.lo + opix * o.cstride + o.coff + co0;
+                    if (nco == 16 && (((o.cstride | (o.coff + co0)) & 7) == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 8) {
+                            *reinterpret_cast<uint4*>(dh + j) = make_uint4(pack_bf16x2(h[j], h[j + 1]), pack_bf16x2(h[j + 2], h[j + 3]),
+                                                                           pack_bf16x2(h[j + 4], h[j + 5]), pack_bf16x2(h[j + 6], h[j + 7]));
+                            *reinterpret_cast<uint4*>(dl + j) = make_uint4(pack_bf16x2(l[j], l[j + 1]), pack_bf16x2(l[j + 2], l[j + 3]),
+                                                                           pack_bf16x2(l[j + 4], l[j + 5]), pack_bf16x2(l[j + 6], l[j + 7]));
+                        }
+                    } else {
+                        for (int j = 0; j < nco; ++j) { dh[j] = h[j]; dl[j] = l[j]; }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)P.tmem_cols) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || !p) return nullptr;
+        fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint32_t* box) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) { n3d_set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return N3D_ERR_CUDA; }
+    cuuint64_t gdim[5], gstr[5];
+    cuuint32_t bdim[5], estr[5];
+    uint64_t stride = 2;
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = 1;
+        stride *= dims[i];
+        if (i < rank - 1) gstr[i] = stride;      // byte stride of dim i+1
+    }
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { n3d_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return N3D_ERR_CUDA; }
+    return N3D_OK;
+}
+
+int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+int* g_err_flag = nullptr;   // device int, lazily allocated once per process; only written when a kernel traps
+
+}  // namespace
+
+extern "C" int n3d_conv_gemm(const N3DConvGemm* p, void* stream) {
+    N3D_CHECK_ARG(p && p->a_hi && p->w_hi, "n3d_conv_gemm: null operand");
+    N3D_CHECK_ARG(p->nprod == 1 || p->nprod == 3, "n3d_conv_gemm: nprod must be 1 or 3");
+    N3D_CHECK_ARG(p->nprod == 1 || (p->a_lo && p->w_lo), "n3d_conv_gemm: nprod 3 needs lo operands");
+    N3D_CHECK_ARG(p->ntaps >= 1 && p->ntaps <= 9, "n3d_conv_gemm: ntaps %d", p->ntaps);
+    N3D_CHECK_ARG(p->Cin >= 8 && p->Cin % 8 == 0, "n3d_conv_gemm: Cin %d must be a multiple of 8 (TMA 16-byte strides)", p->Cin);
+    N3D_CHECK_ARG(p->Cout >= 1 && p->N >= 1 && p->MH >= 1 && p->MW >= 1, "n3d_conv_gemm: bad sizes");
+    N3D_CHECK_ARG(((uintptr_t)p->a_hi & 15) == 0 && ((uintptr_t)p->w_hi & 15) == 0, "n3d_conv_gemm: operands must be 16-byte aligned");
+    N3D_CHECK_ARG(p->mode == 0 || (p->mode == 1 && p->out_f32), "n3d_conv_gemm: bad mode");
+    cudaStream_t st = (cudaStream_t)stream;
+
+    KParams K;
+    memset(&K, 0, sizeof(K));
+    K.N = p->N; K.MH = p->MH; K.MW = p->MW; K.Cout = p->Cout;
+    K.TW = min(16, pow2_ceil(p->MW));
+    K.TH = min(kBlockM / K.TW, pow2_ceil(p->MH));
+    K.TN = kBlockM / (K.TW * K.TH);
+    K.tiles_x = n3d_div_up(p->MW, K.TW); K.tiles_y = n3d_div_up(p->MH, K.TH); K.tiles_i = n3d_div_up(p->N, K.TN);
+    const int tiles_m = K.tiles_x * K.tiles_y * K.tiles_i;
+    // block_n: the largest legal UMMA N (M=128 needs N % 16 == 0) not exceeding Cout, shrunk while the launch would
+    // not fill one wave of the 148 SMs.
+    const int cout16 = ((p->Cout + 15) / 16) * 16;
+    int bn = 16;
+    {
+        const int cands[6] = {256, 128, 96, 64, 32, 16};
+        for (int i = 0; i < 6; ++i) {
+            if (cands[i] > cout16) continue;
+            if (cands[i] == 96 && cout16 % 96 != 0) continue;
+            bn = cands[i];
+            break;
+        }
+        while (bn > 32 && tiles_m * n3d_div_up(p->Cout, bn) < 148) bn = (bn == 96) ? 32 : bn / 2;
+    }
+    K.block_n = bn;
+    K.tiles_n = n3d_div_up(p->Cout, bn);
+    K.acc_stride = max(32, pow2_ceil(bn));
+    K.tmem_cols = 2 * K.acc_stride;
+    K.b_bytes = bn * kBlockK * 2;
+    K.stage_bytes = 2 * kABytes + 2 * K.b_bytes;
+    K.stages = min(6, (200 * 1024) / K.stage_bytes);
+    K.cin_chunks = n3d_div_up(p->Cin, kBlockK);
+    K.ntaps = p->ntaps; K.nprod = p->nprod; K.a_img_stride = p->a_img_mul;
+    for (int i = 0; i < p->ntaps; ++i) {
+        K.taps[i] = p->taps[i];
+        N3D_CHECK_ARG(p->taps[i].wtap >= 0 && p->taps[i].wtap < p->T, "n3d_conv_gemm: tap %d weight slab out of range", i);
+    }
+    K.mode = p->mode; K.dcoef = p->dcoef; K.bias = p->bias; K.noise = p->noise;
+    K.gain = p->gain; K.slope = p->slope; K.clamp = p->clamp;
+    K.out[0] = p->out[0]; K.out[1] = p->out[1];
+    K.out_f32 = p->out_f32; K.f32_cstride = p->f32_cstride; K.f32_coff = p->f32_coff; K.f32_nchw = p->f32_nchw;
+    K.f32_accumulate = p->f32_accumulate;
+    K.oy_mul = p->oy_mul; K.oy_off = p->oy_off; K.ox_mul = p->ox_mul; K.ox_off = p->ox_off; K.OH = p->OH; K.OW = p->OW;
+    if (!g_err_flag) {
+        if (cudaMalloc(&g_err_flag, sizeof(int)) != cudaSuccess) { n3d_set_error("n3d_conv_gemm: cudaMalloc(err flag) failed"); return N3D_ERR_CUDA; }
+        cudaMemset(g_err_flag, 0, sizeof(int));
+    }
+    K.err_flag = g_err_flag;
+
+    const uint64_t adims[4] = {(uint64_t)p->Cin, (uint64_t)p->AW, (uint64_t)p->AH, (uint64_t)p->NI};
+    const uint32_t abox[4] = {(uint32_t)kBlockK, (uint32_t)K.TW, (uint32_t)K.TH, (uint32_t)K.TN};
+    const uint64_t wdims[3] = {(uint64_t)p->Cin, (uint64_t)p->Cout, (uint64_t)p->T};
+    const uint32_t wbox[3] = {(uint32_t)kBlockK, (uint32_t)bn, 1u};
+    int rc;
+    if ((rc = make_tmap(&K.tmA_hi, p->a_hi, 4, adims, abox)) != N3D_OK) return rc;
+    if ((rc = make_tmap(&K.tmB_hi, p->w_hi, 3, wdims, wbox)) != N3D_OK) return rc;
+    if (p->nprod == 3) {
+        if ((rc = make_tmap(&K.tmA_lo, p->a_lo, 4, adims, abox)) != N3D_OK) return rc;
+        if ((rc = make_tmap(&K.tmB_lo, p->w_lo, 3, wdims, wbox)) != N3D_OK) return rc;
+    }
+
+    const int smem = K.stages * K.stage_bytes + 8 * (2 * K.stages + 4) + 16 + 1024;
+    static int smem_configured = 0;
+    if (smem > smem_configured) {
+        if (cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+            n3d_set_error("n3d_conv_gemm: cannot raise dynamic shared memory to 227 KiB");
+            return N3D_ERR_CUDA;
+        }
+        smem_configured = 227 * 1024;
+    }
+    const int total_tiles = tiles_m * K.tiles_n;
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (num_sms <= 0) num_sms = 148;
+    }
+    const int grid = min(total_tiles, num_sms);
+    conv_gemm_kernel<<<grid, kThreads, smem, st>>>(K);
+    N3D_CHECK_LAUNCH("n3d_conv_gemm");
+    return N3D_OK;
+}

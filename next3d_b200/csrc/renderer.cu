@@ -1,0 +1,471 @@
+// Fused volume renderer: ray generation, stratified depths, tri-plane bilinear fetch (+ mean over planes), MLP decoder
+// (32 -> 64 softplus -> 33, sigmoid), coarse compositing weights, importance resampling, sort-merge of coarse + fine
+// samples and final alpha compositing -- one kernel, nothing but the final [N,M,32] / depth / weight-sum leaves the SM.
+// Replaces RaySampler.forward (ray_sampler.py:24-63), ImportanceRenderer.forward (renderer.py:95-268), OSGDecoder.forward
+// (triplane_next3d.py:359-371) and MipRayMarcher2.run_forward (ray_marcher.py:27-66), which materialise
+// [N,3,M*D,32] feature tensors (604 MB per pass at batch 8) in the reference.
+//
+// v1 organisation (SIMT fp32, exact-math transcendental functions):
+//   CTA = RAYS rays x D samples = up to 192 threads.  Gather: one warp per sample, lanes = the 32 channels, so each of the
+//   12 bilinear taps is one coalesced 128-byte line of the channels-last planes.  Decode: one thread per sample, weights
+//   broadcast from shared memory as float4.  Per-ray scans (weights, CDF inversion, merge) run one thread per ray.
+#include "common.cuh"
+#include "../../include/next3d_b200.h"
+
+namespace {
+
+constexpr int kMaxThreads = 192;
+constexpr int kFeat = 32;
+constexpr int kHidden = 64;
+constexpr int kOut = 33;
+constexpr int kRowStride = 33;          // 32 colours + sigma; odd stride => conflict-free per-thread rows
+constexpr int kW1Stride = 36;           // transposed layer-2 weights [64][36] (33 used), float4-aligned
+constexpr int kMaxD = 96;
+
+struct RenderK {
+    N3DRender p;
+    int rays_per_cta;
+    int M;
+    float delta_coarse;
+};
+
+__device__ __forceinline__ float softplus_t(float x) { return x > 20.f ? x : log1pf(expf(x)); }   // torch Softplus(beta 1, threshold 20)
+__device__ __forceinline__ float sigmoid_t(float x) { return 1.f / (1.f + expf(-x)); }
+
+__device__ __forceinline__ float hash_uniform(uint64_t seed, uint64_t idx) {
+    uint64_t z = seed + idx * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (float)(uint32_t)(z >> 40) * (1.0f / 16777216.0f);
+}
+
+// torch.linspace(start, end, steps) for float32: symmetric evaluation around the midpoint
+__device__ __forceinline__ float linspace_at(float start, float end, int steps, int i) {
+    const float step = (end - start) / (float)(steps - 1);
+    return i < steps / 2 ? start + step * (float)i : end - step * (float)(steps - 1 - i);
+}
+
+// bilinear fetch of one plane at grid coords (gx, gy) for channel `lane` (zeros padding, align_corners=False)
+__device__ __forceinline__ float plane_fetch(const float* __restrict__ plane, int PH, int PW, float gx, float gy, int lane) {
+    const float ix = ((gx + 1.f) * (float)PW - 1.f) * 0.5f, iy = ((gy + 1.f) * (float)PH - 1.f) * 0.5f;
+    const float flx = floorf(ix), fly = floorf(iy);
+    const int x0 = (int)flx, y0 = (int)fly;
+    const float fx = ix - flx, fy = iy - fly;
+    float acc = 0.f;
+    const bool xin0 = x0 >= 0 && x0 < PW, xin1 = x0 + 1 >= 0 && x0 + 1 < PW;
+    if (y0 >= 0 && y0 < PH) {
+        const float* r = plane + ((int64_t)y0 * PW) * kFeat + lane;
+        if (xin0) acc += (1.f - fx) * (1.f - fy) * __ldg(r + (int64_t)x0 * kFeat);
+        if (xin1) acc += fx * (1.f - fy) * __ldg(r + (int64_t)(x0 + 1) * kFeat);
+    }
+    if (y0 + 1 >= 0 && y0 + 1 < PH) {
+        const float* r = plane + ((int64_t)(y0 + 1) * PW) * kFeat + lane;
+        if (xin0) acc += (1.f - fx) * fy * __ldg(r + (int64_t)x0 * kFeat);
+        if (xin1) acc += fx * fy * __ldg(r + (int64_t)(x0 + 1) * kFeat);
+    }
+    return acc;
+}
+
+// mean over the three planes of the bilinear features at world point (px,py,pz); plane 0 <- (x,y), 1 <- (x,z), 2 <- (z,y)
+__device__ __forceinline__ float triplane_feature(const float* __restrict__ planes_n, int PH, int PW, float px, float py, float pz, float scale, int lane) {
+    const float x = scale * px, y = scale * py, z = scale * pz;
+    const int64_t ps = (int64_t)PH * PW * kFeat;
+    const float f0 = plane_fetch(planes_n, PH, PW, x, y, lane);
+    const float f1 = plane_fetch(planes_n + ps, PH, PW, x, z, lane);
+    const float f2 = plane_fetch(planes_n + 2 * ps, PH, PW, z, y, lane);
+    return ((f0 + f1) + f2) / 3.f;
+}
+
+// decode one sample in place: row[0..31] features -> row[0..31] rgb, row[32] sigma
+__device__ __forceinline__ void decode_row(float* __restrict__ row, const float* __restrict__ sW0, const float* __restrict__ sB0,
+                                           const float* __restrict__ sW1t, const float* __restrict__ sB1) {
+    float f[kFeat];
+#pragma unroll
+    for (int c = 0; c < kFeat; ++c) f[c] = row[c];
+    float o[kW1Stride];
+#pragma unroll
+    for (int j = 0; j < kW1Stride; ++j) o[j] = j < kOut ? sB1[j] : 0.f;
+#pragma unroll 2
+    for (int j = 0; j < kHidden; ++j) {
+        float a = sB0[j];
+        const float4* w = reinterpret_cast<const float4*>(sW0 + j * kFeat);
+#pragma unroll
+        for (int c4 = 0; c4 < kFeat / 4; ++c4) {
+            const float4 wv = w[c4];
+            a += wv.x * f[c4 * 4] + wv.y * f[c4 * 4 + 1] + wv.z * f[c4 * 4 + 2] + wv.w * f[c4 * 4 + 3];
+        }
+        const float h = softplus_t(a);
+        const float4* w1 = reinterpret_cast<const float4*>(sW1t + j * kW1Stride);
+#pragma unroll
+        for (int o4 = 0; o4 < kW1Stride / 4; ++o4) {
+            const float4 wv = w1[o4];
+            o[o4 * 4] += wv.x * h; o[o4 * 4 + 1] += wv.y * h; o[o4 * 4 + 2] += wv.z * h; o[o4 * 4 + 3] += wv.w * h;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < kFeat; ++c) row[c] = sigmoid_t(o[1 + c]) * 1.002f - 0.001f;
+    row[32] = o[0];
+}
+
+__device__ __forceinline__ void load_decoder(const float* w0, const float* b0, const float* w1, const float* b1, float* sW0, float* sB0,
+                                             float* sW1t, float* sB1) {
+    for (int i = threadIdx.x; i < kHidden * kFeat; i += blockDim.x) sW0[i] = w0[i];
+    for (int i = threadIdx.x; i < kHidden; i += blockDim.x) sB0[i] = b0[i];
+    for (int i = threadIdx.x; i < kHidden * kW1Stride; i += blockDim.x) {
+        const int j = i / kW1Stride, o = i % kW1Stride;
+        sW1t[i] = o < kOut ? w1[o * kHidden + j] : 0.f;
+    }
+    for (int i = threadIdx.x; i < kW1Stride; i += blockDim.x) sB1[i] = i < kOut ? b1[i] : 0.f;
+}
+
+// MipRayMarcher2 weights for one sorted sample list (thread-sequential): w[k], k < cnt-1.  Returns sum of weights.
+template <typename DepthAt, typename SigmaAt>
+__device__ __forceinline__ float march_weights(int cnt, DepthAt depth_at, SigmaAt sigma_at, float* w) {
+    float T = 1.f, wsum = 0.f;
+    float t_prev = depth_at(0), s_prev = sigma_at(0);
+    for (int k = 0; k < cnt - 1; ++k) {
+        const float t_next = depth_at(k + 1), s_next = sigma_at(k + 1);
+        const float delta = t_next - t_prev;
+        const float dens = softplus_t((s_prev + s_next) / 2.f - 1.f);
+        const float alpha = 1.f - expf(-(dens * delta));
+        const float wk = alpha * T;
+        w[k] = wk;
+        wsum += wk;
+        T *= (1.f - alpha + 1e-10f);
+        t_prev = t_next; s_prev = s_next;
+    }
+    return wsum;
+}
+
+__global__ void __launch_bounds__(kMaxThreads) render_kernel(const RenderK K) {
+    extern __shared__ __align__(16) float smem[];
+    const N3DRender& P = K.p;
+    const int Dc = P.depth_coarse, Df = P.depth_fine, R = K.rays_per_cta;
+    const int Dt = Dc + Df;
+    // ---- shared memory carve-up
+    float* sW0 = smem;                                   // [64][32]
+    float* sW1t = sW0 + kHidden * kFeat;                 // [64][36]
+    float* sB0 = sW1t + kHidden * kW1Stride;             // [64]
+    float* sB1 = sB0 + kHidden;                          // [36]
+    float* sC = sB1 + kW1Stride;                         // coarse rows [R*Dc][33]
+    float* sF = sC + R * Dc * kRowStride;                // fine rows   [R*Df][33]
+    float* sTc = sF + R * Df * kRowStride;               // coarse depths [R][Dc]
+    float* sTf = sTc + R * Dc;                           // fine depths   [R][Df]
+    float* sWgt = sTf + R * Df;                          // weights [R][Dt]
+    float* sRay = sWgt + R * Dt;                         // [R][8]: origin xyz, dir xyz
+    unsigned char* sOrd = reinterpret_cast<unsigned char*>(sRay + R * 8);   // [R][Dt] merged order
+    __shared__ float s_min[kMaxThreads / 32], s_max[kMaxThreads / 32];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int64_t ray0 = (int64_t)blockIdx.x * R;        // global ray index = n*M + m
+    const int64_t total_rays = (int64_t)P.N * K.M;
+
+    load_decoder(P.w0, P.b0, P.w1, P.b1, sW0, sB0, sW1t, sB1);
+
+    // ---- rays (ray_sampler.py:43-63)
+    if (tid < R) {
+        const int64_t gr = ray0 + tid;
+        if (gr < total_rays) {
+            const int n = (int)(gr / K.M), m = (int)(gr % K.M);
+            const int i = m / P.res, j = m % P.res;
+            const float inv = 1.f / (float)P.res, half = 0.5f / (float)P.res;
+            const float xc = (float)j * inv + half, yc = (float)i * inv + half;
+            const float* I = P.intrinsics + n * 9;
+            const float fx = I[0], sk = I[1], cx = I[2], fy = I[4], cy = I[5];
+            const float xl = (xc - cx + cy * sk / fy - sk * yc / fy) / fx;
+            const float yl = (yc - cy) / fy;
+            const float* C = P.cam2world + n * 16;
+            float wv[3], o[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                wv[a] = C[a * 4] * xl + C[a * 4 + 1] * yl + C[a * 4 + 2] + C[a * 4 + 3];
+                o[a] = C[a * 4 + 3];
+                wv[a] -= o[a];
+            }
+            const float nrm = fmaxf(sqrtf(wv[0] * wv[0] + wv[1] * wv[1] + wv[2] * wv[2]), 1e-12f);
+            float* r = sRay + tid * 8;
+            r[0] = o[0]; r[1] = o[1]; r[2] = o[2];
+            r[3] = wv[0] / nrm; r[4] = wv[1] / nrm; r[5] = wv[2] / nrm;
+        }
+    }
+    // ---- coarse depths (renderer.py:203-205)
+    for (int s = tid; s < R * Dc; s += blockDim.x) {
+        const int r = s / Dc, k = s % Dc;
+        const int64_t gr = ray0 + r;
+        float t = 0.f;
+        if (gr < total_rays) {
+            const float u = P.u_coarse ? __ldg(P.u_coarse + gr * Dc + k) : hash_uniform(P.seed, (uint64_t)(gr * Dc + k));
+            t = linspace_at(P.ray_start, P.ray_end, Dc, k) + u * K.delta_coarse;
+        }
+        sTc[s] = t;
+    }
+    __syncthreads();
+
+    const float scale = 2.f / P.box_warp;
+    const int64_t plane_img = (int64_t)3 * P.PH * P.PW * kFeat;
+
+    // ---- coarse pass: gather (warp per sample) then decode (thread per sample)
+    for (int s = warp; s < R * Dc; s += nwarps) {
+        const int r = s / Dc;
+        const int64_t gr = ray0 + r;
+        float feat = 0.f;
+        if (gr < total_rays) {
+            const float* ry = sRay + r * 8;
+            const float t = sTc[s];
+            feat = triplane_feature(P.planes + (gr / K.M) * plane_img, P.PH, P.PW, ry[0] + t * ry[3], ry[1] + t * ry[4], ry[2] + t * ry[5], scale, lane);
+        }
+        sC[s * kRowStride + lane] = feat;
+    }
+    __syncthreads();
+    for (int s = tid; s < R * Dc; s += blockDim.x) decode_row(sC + s * kRowStride, sW0, sB0, sW1t, sB1);
+    __syncthreads();
+
+    // ---- per ray: coarse weights -> smoothed pdf -> inverse-CDF samples (renderer.py:209-268)
+    if (tid < R && ray0 + tid < total_rays && Df > 0) {
+        const int r = tid;
+        const int64_t gr = ray0 + r;
+        float* w = sWgt + r * Dt;               // scratch: weights [Dc-1], then pdf/cdf
+        const float* tc = sTc + r * Dc;
+        const float* rows = sC + (r * Dc) * kRowStride;
+        march_weights(Dc, [&](int k) { return tc[k]; }, [&](int k) { return rows[k * kRowStride + 32]; }, w);
+        // max_pool1d(k2,s1,pad1) -> avg_pool1d(k2,s1) -> +0.01 ; keep entries [1:-1] => Dc-3 pdf weights, + 1e-5
+        const int nw = Dc - 3;
+        float* cdf = w + Dc;                     // [nw+1] (Dt - Dc = Df >= nw + 1 is checked on the host)
+        float total = 0.f;
+        for (int i = 0; i < nw; ++i) {
+            const int q = i + 1;                 // index into the avg-pooled array (length Dc-1)
+            const float mp0 = fmaxf(w[q - 1], w[q]);                                   // maxpool[q]   = max(w[q-1], w[q])
+            const float mp1 = q + 1 <= Dc - 2 ? fmaxf(w[q], w[q + 1]) : w[q];          // maxpool[q+1] = max(w[q], w[q+1]) (last: w[Dc-2])
+            const float v = (mp0 + mp1) * 0.5f + 0.01f + 1e-5f;
+            cdf[i + 1] = v;
+            total += v;
+        }
+        cdf[0] = 0.f;
+        float run = 0.f;
+        for (int i = 0; i < nw; ++i) { run += cdf[i + 1] / total; cdf[i + 1] = run; }
+        float* tf = sTf + r * Df;
+        for (int j = 0; j < Df; ++j) {
+            const float u = P.u_fine ? __ldg(P.u_fine + gr * Df + j) : hash_uniform(P.seed ^ 0xA5A5A5A5DEADBEEFull, (uint64_t)(gr * Df + j));
+            int lo = 0, hi = nw + 1;             // searchsorted(cdf, u, right=True): first index with cdf[idx] > u
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (cdf[mid] <= u) lo = mid + 1; else hi = mid; }
+            const int below = max(lo - 1, 0), above = min(lo, nw);
+            const float cb = cdf[below], ca = cdf[above];
+            const float bb = 0.5f * (tc[below] + tc[below + 1]), ba = 0.5f * (tc[above] + tc[above + 1]);
+            float denom = ca - cb;
+            if (denom < 1e-5f) denom = 1.f;
+            tf[j] = bb + (u - cb) / denom * (ba - bb);
+        }
+    }
+    __syncthreads();
+
+    // ---- fine pass
+    for (int s = warp; s < R * Df; s += nwarps) {
+        const int r = s / Df;
+        const int64_t gr = ray0 + r;
+        float feat = 0.f;
+        if (gr < total_rays) {
+            const float* ry = sRay + r * 8;
+            const float t = sTf[s];
+            feat = triplane_feature(P.planes + (gr / K.M) * plane_img, P.PH, P.PW, ry[0] + t * ry[3], ry[1] + t * ry[4], ry[2] + t * ry[5], scale, lane);
+        }
+        sF[s * kRowStride + lane] = feat;
+    }
+    __syncthreads();
+    for (int s = tid; s < R * Df; s += blockDim.x) decode_row(sF + s * kRowStride, sW0, sB0, sW1t, sB1);
+    __syncthreads();
+
+    // ---- per ray: stable sort-merge of coarse (already sorted) and fine depths, final weights (renderer.py:164-182)
+    float dmin = INFINITY, dmax = -INFINITY;
+    if (tid < R && ray0 + tid < total_rays) {
+        const int r = tid;
+        const float* tc = sTc + r * Dc;
+        const float* tf = sTf + r * Df;
+        unsigned char* ord = sOrd + r * Dt;
+        // insertion sort of fine indices by depth (stable), kept in the tail of `ord`
+        unsigned char* fo = ord + Dc;
+        for (int j = 0; j < Df; ++j) {
+            const float v = tf[j];
+            int q = j;
+            while (q > 0 && tf[fo[q - 1]] > v) { fo[q] = fo[q - 1]; --q; }
+            fo[q] = (unsigned char)j;
+        }
+        // merge: on ties the coarse sample comes first (it precedes the fine ones in the concatenated tensor)
+        int a = 0, b = 0;
+        unsigned char tmp[2 * kMaxD];
+        for (int k = 0; k < Dt; ++k) {
+            const bool take_c = b >= Df || (a < Dc && tc[a] <= tf[fo[b]]);
+            tmp[k] = take_c ? (unsigned char)(a++) : (unsigned char)(Dc + fo[b++]);
+        }
+        for (int k = 0; k < Dt; ++k) ord[k] = tmp[k];
+        const float* rc = sC + (r * Dc) * kRowStride;
+        const float* rf = sF + (r * Df) * kRowStride;
+        auto depth_at = [&](int k) { const int o = ord[k]; return o < Dc ? tc[o] : tf[o - Dc]; };
+        auto sigma_at = [&](int k) { const int o = ord[k]; return o < Dc ? rc[o * kRowStride + 32] : rf[(o - Dc) * kRowStride + 32]; };
+        float* w = sWgt + r * Dt;
+        const float wsum = march_weights(Dt, depth_at, sigma_at, w);
+        float dacc = 0.f;
+        for (int k = 0; k < Dt - 1; ++k) dacc += w[k] * ((depth_at(k) + depth_at(k + 1)) / 2.f);
+        float depth = dacc / wsum;
+        if (isnan(depth)) depth = INFINITY;                         // nan_to_num(nan=inf); the clamp kernel finishes the job
+        const int64_t gr = ray0 + r;
+        P.depth[gr] = depth;
+        P.wsum[gr] = wsum;
+        dmin = fminf(depth_at(0), dmin);
+        dmax = fmaxf(depth_at(Dt - 1), dmax);
+    }
+    __syncthreads();
+
+    // ---- composite colours: warp per ray, lanes = channels
+    for (int r = warp; r < R; r += nwarps) {
+        const int64_t gr = ray0 + r;
+        if (gr >= total_rays) continue;
+        const unsigned char* ord = sOrd + r * Dt;
+        const float* w = sWgt + r * Dt;
+        const float* rc = sC + (r * Dc) * kRowStride;
+        const float* rf = sF + (r * Df) * kRowStride;
+        auto color_at = [&](int k) { const int o = ord[k]; return o < Dc ? rc[o * kRowStride + lane] : rf[(o - Dc) * kRowStride + lane]; };
+        float acc = 0.f, wtot = 0.f;
+        float c_prev = color_at(0);
+        for (int k = 0; k < Dt - 1; ++k) {
+            const float c_next = color_at(k + 1);
+            acc += w[k] * ((c_prev + c_next) / 2.f);
+            wtot += w[k];
+            c_prev = c_next;
+        }
+        if (P.white_back) acc = acc + 1.f - wtot;
+        P.rgb[gr * kFeat + lane] = acc * 2.f - 1.f;
+    }
+
+    // ---- batch-global depth range (ray_marcher.py:54): warp + block reduce, then one atomic pair per CTA
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+        dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    }
+    if (lane == 0) { s_min[warp] = dmin; s_max[warp] = dmax; }
+    __syncthreads();
+    if (tid == 0 && P.depth_minmax) {
+        for (int i = 1; i < nwarps; ++i) { dmin = fminf(dmin, s_min[i]); dmax = fmaxf(dmax, s_max[i]); }
+        // depths are positive (ray_start > 0): IEEE ordering == signed-int ordering
+        if (dmin < INFINITY) atomicMin(reinterpret_cast<int*>(P.depth_minmax), __float_as_int(dmin));
+        if (dmax > -INFINITY) atomicMax(reinterpret_cast<int*>(P.depth_minmax) + 1, __float_as_int(dmax));
+    }
+}
+
+__global__ void __launch_bounds__(256) depth_clamp_kernel(float* __restrict__ depth, int64_t n, const float* __restrict__ mm) {
+    const float lo = mm[0], hi = mm[1];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float d = depth[i];
+        if (isnan(d)) d = INFINITY;
+        depth[i] = fminf(fmaxf(d, lo), hi);
+    }
+}
+
+// run_model on arbitrary points: CTA of 192 threads handles 192 points
+__global__ void __launch_bounds__(kMaxThreads) sample_points_kernel(const float* __restrict__ planes, int N, int PH, int PW, const float* __restrict__ coords,
+                                                                   int64_t Pn, float scale, const float* w0, const float* b0, const float* w1,
+                                                                   const float* b1, float* __restrict__ sigma, float* __restrict__ rgb) {
+    extern __shared__ __align__(16) float smem[];
+    float* sW0 = smem;
+    float* sW1t = sW0 + kHidden * kFeat;
+    float* sB0 = sW1t + kHidden * kW1Stride;
+    float* sB1 = sB0 + kHidden;
+    float* sC = sB1 + kW1Stride;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    load_decoder(w0, b0, w1, b1, sW0, sB0, sW1t, sB1);
+    __syncthreads();
+    const int64_t total = (int64_t)N * Pn;
+    const int64_t plane_img = (int64_t)3 * PH * PW * kFeat;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < total; base += (int64_t)gridDim.x * blockDim.x) {
+        for (int s = warp; s < (int)blockDim.x; s += nwarps) {
+            const int64_t g = base + s;
+            float feat = 0.f;
+            if (g < total) {
+                const float* c = coords + g * 3;
+                feat = triplane_feature(planes + (g / Pn) * plane_img, PH, PW, __ldg(c), __ldg(c + 1), __ldg(c + 2), scale, lane);
+            }
+            sC[s * kRowStride + lane] = feat;
+        }
+        __syncthreads();
+        if (base + tid < total) {
+            decode_row(sC + tid * kRowStride, sW0, sB0, sW1t, sB1);
+            sigma[base + tid] = sC[tid * kRowStride + 32];
+        }
+        __syncthreads();
+        if (rgb) {
+            for (int s = warp; s < (int)blockDim.x; s += nwarps)
+                if (base + s < total) rgb[(base + s) * kFeat + lane] = sC[s * kRowStride + lane];
+        }
+        __syncthreads();
+    }
+}
+
+size_t render_smem_bytes(int R, int Dc, int Df) {
+    const int Dt = Dc + Df;
+    size_t fl = (size_t)kHidden * kFeat + kHidden * kW1Stride + kHidden + kW1Stride + (size_t)R * Dc * kRowStride + (size_t)R * Df * kRowStride +
+                (size_t)R * Dc + (size_t)R * Df + (size_t)R * Dt + (size_t)R * 8;
+    return fl * sizeof(float) + (size_t)R * Dt + 16;
+}
+}  // namespace
+
+extern "C" int n3d_render_rays(const N3DRender* p, void* stream) {
+    N3D_CHECK_ARG(p && p->planes && p->cam2world && p->intrinsics && p->w0 && p->b0 && p->w1 && p->b1 && p->rgb && p->depth && p->wsum,
+                  "n3d_render_rays: null pointer");
+    N3D_CHECK_ARG(p->depth_coarse >= 4 && p->depth_coarse <= kMaxD && p->depth_fine >= 0 && p->depth_fine <= kMaxD,
+                  "n3d_render_rays: depth resolutions (%d, %d) outside [4, %d]", p->depth_coarse, p->depth_fine, kMaxD);
+    N3D_CHECK_ARG(p->depth_fine == 0 || p->depth_fine >= p->depth_coarse - 2, "n3d_render_rays: depth_fine must be >= depth_coarse - 2 (scratch layout)");
+    N3D_CHECK_ARG(p->depth_fine > 0, "n3d_render_rays: depth_fine == 0 (coarse-only rendering) is not supported yet");
+    N3D_CHECK_ARG(p->res >= 1 && p->N >= 1 && p->ray_start > 0.f && p->ray_end > p->ray_start, "n3d_render_rays: bad ray setup");
+    RenderK K;
+    K.p = *p;
+    K.M = p->res * p->res;
+    const int dmax = p->depth_coarse > p->depth_fine ? p->depth_coarse : p->depth_fine;
+    K.rays_per_cta = kMaxThreads / dmax;
+    if (K.rays_per_cta < 1) K.rays_per_cta = 1;
+    K.delta_coarse = (float)(((double)p->ray_end - (double)p->ray_start) / (double)(p->depth_coarse - 1));
+    const int threads = ((K.rays_per_cta * dmax + 31) / 32) * 32;
+    const size_t smem = render_smem_bytes(K.rays_per_cta, p->depth_coarse, p->depth_fine);
+    static size_t configured = 0;
+    if (smem > configured) {
+        if (cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+            n3d_set_error("n3d_render_rays: cannot raise dynamic shared memory");
+            return N3D_ERR_CUDA;
+        }
+        configured = 200 * 1024;
+    }
+    const int64_t total_rays = (int64_t)p->N * K.M;
+    const int grid = (int)((total_rays + K.rays_per_cta - 1) / K.rays_per_cta);
+    render_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(K);
+    N3D_CHECK_LAUNCH("n3d_render_rays");
+    return N3D_OK;
+}
+
+extern "C" int n3d_depth_clamp(float* depth, int64_t n, const float* depth_minmax, void* stream) {
+    N3D_CHECK_ARG(depth && depth_minmax && n >= 0, "n3d_depth_clamp: bad args");
+    if (n == 0) return N3D_OK;
+    depth_clamp_kernel<<<(int)((n + 255) / 256 > 1184 ? 1184 : (n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(depth, n, depth_minmax);
+    N3D_CHECK_LAUNCH("n3d_depth_clamp");
+    return N3D_OK;
+}
+
+extern "C" int n3d_sample_points(const float* planes, int N, int PH, int PW, const float* coords, int64_t P, float box_warp,
+                                 const float* w0, const float* b0, const float* w1, const float* b1, float* sigma, float* rgb,
+                                 void* stream) {
+    N3D_CHECK_ARG(planes && coords && w0 && b0 && w1 && b1 && sigma && N >= 1 && P >= 1, "n3d_sample_points: bad args");
+    const size_t smem = ((size_t)kHidden * kFeat + kHidden * kW1Stride + kHidden + kW1Stride + (size_t)kMaxThreads * kRowStride) * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(sample_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess) {
+            n3d_set_error("n3d_sample_points: cannot raise dynamic shared memory");
+            return N3D_ERR_CUDA;
+        }
+        configured = true;
+    }
+    const int64_t total = (int64_t)N * P;
+    int64_t grid = (total + kMaxThreads - 1) / kMaxThreads;
+    if (grid > 148 * 16) grid = 148 * 16;
+    sample_points_kernel<<<(int)grid, kMaxThreads, smem, (cudaStream_t)stream>>>(planes, N, PH, PW, coords, P, 2.f / box_warp, w0, b0, w1, b1, sigma, rgb);
+    N3D_CHECK_LAUNCH("n3d_sample_points");
+    return N3D_OK;
+}
