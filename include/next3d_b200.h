@@ -70,14 +70,19 @@ int n3d_filtered_lrelu(const void* x, const float* fu, const float* fd, const vo
  * ---------------------------------------------------------------------------------------------------------- */
 
 /* All style vectors of all modulated layers in one launch (FullyConnectedLayer affine, networks_stylegan2.py:303,315
- * and ToRGB's weight_gain :354):  styles[n, r] = (dot(ws[n, widx[r], :], A[r, :]) / sqrt(wdim) + b[r]) * scale[r]. */
+ * and ToRGB's weight_gain :354).  Row r of the concatenated affine matrix belongs to input channel i of some layer:
+ *   styles[row_ooff[r] + n * row_cin[r]] = (dot(ws[n, widx[r], :], A[r, :]) / sqrt(wdim) + b[r]) * scale[r]
+ * so that every layer owns a dense [N, Cin] block (row_ooff[r] = layer_base * N + i). */
 int n3d_styles(const float* ws, int N, int num_ws, int wdim, const float* affine_w, const float* affine_b,
-               const int32_t* row_widx, const float* row_scale, float* styles, int rows, void* stream);
+               const int32_t* row_widx, const float* row_scale, const int64_t* row_ooff, const int32_t* row_cin,
+               float* styles, int rows, void* stream);
 
-/* Demodulation coefficients of all layers in one launch (networks_stylegan2.py:65):
- *   dcoef[n, r] = rsqrt(sum_i styles[n, soff[r] + i]^2 * wsq[woff[r] + i] + 1e-8),  wsq[o,i] = sum_k W[o,i,k]^2. */
-int n3d_demod(const float* styles, int style_rows, const float* wsq, const int64_t* row_woff, const int32_t* row_cin,
-              const int32_t* row_soff, float* dcoef, int rows, int N, void* stream);
+/* Demodulation coefficients of all layers in one launch (networks_stylegan2.py:65).  Row r = output channel o of a layer:
+ *   dcoef[row_ooff[r] + n*row_cout[r]] = rsqrt(sum_i styles[row_soff[r] + n*row_cin[r] + i]^2 * wsq[row_woff[r] + i] + 1e-8),
+ * wsq[o,i] = sum_k W[o,i,k]^2 (dense [N, Cout] block per layer). */
+int n3d_demod(const float* styles, const float* wsq, const int64_t* row_woff, const int32_t* row_cin,
+              const int64_t* row_soff, const int64_t* row_ooff, const int32_t* row_cout, float* dcoef, int rows, int N,
+              void* stream);
 
 typedef struct {
     int8_t dy, dx;        /* input pixel offset of this tap relative to the output-tile pixel */
@@ -113,6 +118,7 @@ typedef struct {
     const float* dcoef;                      /* [N, Cout] or NULL */
     const float* bias;                       /* [Cout] or NULL */
     const float* noise;                      /* [OH, OW] (already multiplied by noise_strength) or NULL */
+    int64_t noise_nstride;                   /* 0 = one noise map shared by the batch ('const'), OH*OW = per-sample ('random') */
     float gain, slope, clamp;                /* slope 1 = linear; clamp < 0 = none */
     N3DSplitOut out[2];
     float* out_f32; int32_t f32_cstride, f32_coff, f32_nchw, f32_accumulate;
@@ -129,16 +135,17 @@ int n3d_modulate_split(const float* x, int64_t npix_per_img, int N, int C, const
  * raw [(2H+1),(2W+1)] transposed-conv output (fp32 NHWC) -> 4x4 FIR [1,3,3,1]^2/64 * 4, pad 1 -> [2H,2W], then the
  * same epilogue as n3d_conv_gemm mode 0. */
 int n3d_fir_up_epilogue(const float* raw, int N, int H2, int W2, int C, const float* dcoef, const float* bias,
-                        const float* noise, float gain, float slope, float clamp, const N3DSplitOut out[2],
-                        float* out_f32, int f32_cstride, int f32_coff, void* stream);
+                        const float* noise, int64_t noise_nstride, float gain, float slope, float clamp,
+                        const N3DSplitOut out[2], float* out_f32, int f32_cstride, int f32_coff, void* stream);
 
 /* First half of a down-sampling conv (conv2d_resample.py:108-111): fp32 NHWC [H,W] -> FIR pad (2,2,2,2) -> [(H+1),(W+1)]
  * -> split bf16, de-interleaved by pixel parity into 4 sub-images [4, N, SH, SW, C] (parity (y&1)*2 + (x&1), pixel
  * (y>>1, x>>1)), SH = (H+2)/2, so that the stride-2 conv becomes 9 unit-stride taps. */
 int n3d_fir_down_split(const float* x, int N, int H, int W, int C, void* hi, void* lo, void* stream);
 
-/* upfirdn2d.upsample2d on an fp32 NHWC image (up 2, pad (2,1), gain 4; networks_stylegan2.py:577). */
-int n3d_upsample2d_nhwc(const float* x, int N, int H, int W, int C, float* y, void* stream);
+/* upfirdn2d.upsample2d on an fp32 NHWC image (up 2, pad (2,1), gain 4; networks_stylegan2.py:577); y is NHWC, or NCHW
+ * when y_nchw != 0 (used for the final image). */
+int n3d_upsample2d_nhwc(const float* x, int N, int H, int W, int C, float* y, int y_nchw, void* stream);
 /* upfirdn2d.downsample2d on an fp32 NHWC image (pad (1,1), down 2; networks_stylegan2_styleunet.py:109). */
 int n3d_downsample2d_nhwc(const float* x, int N, int H, int W, int C, float* y, void* stream);
 
@@ -164,7 +171,7 @@ int n3d_rasterize(const float* verts, const int32_t* faces, int NM, int V, int F
  *   uv = sum_k bary_k * face_uv[f,k,:] (0 where nothing is visible); value = bilinear(texture[n], uv) (grid_sample, zeros
  *   padding, align_corners False); alpha = bilinear(eye_mask, uv) * visible.
  * pix_to_face / bary are [N*4,H,W(,3)] with image index n*4 + view; face_uv [F,3,2]; texture NHWC [N,TH,TW,C<=32];
- * eye_mask [MH,MW].  Outputs: tex_planes NHWC [N,3,H,W,C] = (view0, view1 + view2, view3) and alpha [N,3,H,W] =
+ * eye_mask [MH,MW].  Outputs (plane-major): tex_planes [3,N,H,W,C] = (view0, view1 + view2, view3) and alpha [3,N,H,W] =
  * (view0, view1, view3) -- the reference's `alpha[1] | alpha[1]` quirk (:226) means view 2's alpha is never used. */
 int n3d_uv_sample(const int32_t* pix_to_face, const float* bary, const float* face_uv, const float* texture,
                   const float* eye_mask, int N, int H, int W, int TH, int TW, int C, int MH, int MW,
@@ -186,8 +193,8 @@ int n3d_resize_aa(const float* src, int N, int SH, int SW, int C, const int32_t*
                   const int32_t* dst_box, const float* style, void* hi, void* lo, void* stream);
 
 /* planes[n,p,y,x,c] = tex[n,p,y,x,c] * alpha[n,p,y,x] + static[n,y,x,p*32+c] * (1 - alpha)  (triplane_next3d.py:171-174);
- * tex for plane 0 = blended_front NHWC [N,H,W,32] (neural-blending output), planes 1,2 = tex_planes[:,1:], alpha [N,3,H,W],
- * static_planes NHWC [N,H,W,96]; planes out channels-last [N,3,H,W,32]. */
+ * tex for plane 0 = blended_front NHWC [N,H,W,32] (neural-blending output), planes 1,2 = tex_planes[1:] (plane-major
+ * [3,N,H,W,32]), alpha [3,N,H,W], static_planes NHWC [N,H,W,96]; planes out channels-last [N,3,H,W,32]. */
 int n3d_blend_planes(const float* blended_front, const float* tex_planes, const float* alpha, const float* static_planes,
                      int N, int H, int W, float* planes, void* stream);
 

@@ -37,7 +37,7 @@ class ConvGemm(C.Structure):
         ('N', I32), ('MH', I32), ('MW', I32), ('a_img_mul', I32),
         ('ntaps', I32), ('taps', ConvTap * 9),
         ('nprod', I32), ('mode', I32),
-        ('dcoef', P), ('bias', P), ('noise', P),
+        ('dcoef', P), ('bias', P), ('noise', P), ('noise_nstride', I64),
         ('gain', F32), ('slope', F32), ('clamp', F32),
         ('out', SplitOut * 2),
         ('out_f32', P), ('f32_cstride', I32), ('f32_coff', I32), ('f32_nchw', I32), ('f32_accumulate', I32),
@@ -62,13 +62,13 @@ _SIGNATURES = {
     'n3d_bias_act': ([P, P, P, C.c_int, I64, C.c_int, C.c_int, C.c_int, F32, F32, F32, P], C.c_int),
     'n3d_upfirdn2d': ([P, P, P, C.c_int] + [C.c_int] * 4 + [C.POINTER(I64), C.POINTER(I64)] + [C.c_int] * 10 + [C.c_int, F32, C.c_int, C.c_int, P], C.c_int),
     'n3d_filtered_lrelu': ([P, P, P, P, P, P, C.c_int] + [C.c_int] * 14 + [F32, F32, F32, C.c_int, C.c_int, C.c_int, P], C.c_int),
-    'n3d_styles': ([P, C.c_int, C.c_int, C.c_int, P, P, P, P, P, C.c_int, P], C.c_int),
-    'n3d_demod': ([P, C.c_int, P, P, P, P, P, C.c_int, C.c_int, P], C.c_int),
+    'n3d_styles': ([P, C.c_int, C.c_int, C.c_int, P, P, P, P, P, P, P, C.c_int, P], C.c_int),
+    'n3d_demod': ([P, P, P, P, P, P, P, P, C.c_int, C.c_int, P], C.c_int),
     'n3d_conv_gemm': ([C.POINTER(ConvGemm), P], C.c_int),
     'n3d_modulate_split': ([P, I64, C.c_int, C.c_int, P, P, P, C.c_int, C.c_int, P], C.c_int),
-    'n3d_fir_up_epilogue': ([P, C.c_int, C.c_int, C.c_int, C.c_int, P, P, P, F32, F32, F32, C.POINTER(SplitOut), P, C.c_int, C.c_int, P], C.c_int),
+    'n3d_fir_up_epilogue': ([P, C.c_int, C.c_int, C.c_int, C.c_int, P, P, P, I64, F32, F32, F32, C.POINTER(SplitOut), P, C.c_int, C.c_int, P], C.c_int),
     'n3d_fir_down_split': ([P, C.c_int, C.c_int, C.c_int, C.c_int, P, P, P], C.c_int),
-    'n3d_upsample2d_nhwc': ([P, C.c_int, C.c_int, C.c_int, C.c_int, P, P], C.c_int),
+    'n3d_upsample2d_nhwc': ([P, C.c_int, C.c_int, C.c_int, C.c_int, P, C.c_int, P], C.c_int),
     'n3d_downsample2d_nhwc': ([P, C.c_int, C.c_int, C.c_int, C.c_int, P, P], C.c_int),
     'n3d_transform_points': ([P, C.c_int, C.c_int, P, C.c_int, F32, C.c_int, P, P], C.c_int),
     'n3d_rasterize': ([P, P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, P, P, P], C.c_int),

@@ -34,7 +34,7 @@ struct KParams {
     int cin_chunks, ntaps, nprod, a_img_stride;
     N3DConvTap taps[9];
     int mode;
-    const float* dcoef; const float* bias; const float* noise;
+    const float* dcoef; const float* bias; const float* noise; int64_t noise_nstride;
     float gain, slope, clamp;
     N3DSplitOut out[2];
     float* out_f32; int f32_cstride, f32_coff, f32_nchw, f32_accumulate;
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             const bool valid = (n < P.N) && (y < P.MH) && (x < P.MW) && (oy < P.OH) && (ox < P.OW);
             const int64_t opix = ((int64_t)n * P.OH + oy) * P.OW + ox;
             float nz = 0.f;
-            if (valid && P.noise) nz = __ldg(P.noise + (int64_t)oy * P.OW + ox);
+            if (valid && P.noise) nz = __ldg(P.noise + (int64_t)n * P.noise_nstride + (int64_t)oy * P.OW + ox);
 
             mbar_wait(tfull_bar(acc), acc_ph, P.err_flag, 4);
             tc_fence_after();
@@ -395,7 +395,7 @@ extern "C" int n3d_conv_gemm(const N3DConvGemm* p, void* stream) {
         K.taps[i] = p->taps[i];
         N3D_CHECK_ARG(p->taps[i].wtap >= 0 && p->taps[i].wtap < p->T, "n3d_conv_gemm: tap %d weight slab out of range", i);
     }
-    K.mode = p->mode; K.dcoef = p->dcoef; K.bias = p->bias; K.noise = p->noise;
+    K.mode = p->mode; K.dcoef = p->dcoef; K.bias = p->bias; K.noise = p->noise; K.noise_nstride = p->noise_nstride;
     K.gain = p->gain; K.slope = p->slope; K.clamp = p->clamp;
     K.out[0] = p->out[0]; K.out[1] = p->out[1];
     K.out_f32 = p->out_f32; K.f32_cstride = p->f32_cstride; K.f32_coff = p->f32_coff; K.f32_nchw = p->f32_nchw;

@@ -20,9 +20,11 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // ---------------------------------------------------------------------------------------------- styles / demod
 // one warp per (row, n): 512-long dot product with float4 loads
+// output layout: every layer owns a dense [N, Cin] block: styles[ooff[r] + n * cin[r]]
 __global__ void __launch_bounds__(256) styles_kernel(const float* __restrict__ ws, int N, int num_ws, int wdim,
                                                      const float* __restrict__ A, const float* __restrict__ b,
                                                      const int* __restrict__ widx, const float* __restrict__ scale,
+                                                     const int64_t* __restrict__ ooff, const int* __restrict__ cin,
                                                      float* __restrict__ styles, int rows) {
     const int lane = threadIdx.x & 31;
     const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -39,26 +41,29 @@ __global__ void __launch_bounds__(256) styles_kernel(const float* __restrict__ w
                 acc += a.x * w.x + a.y * w.y + a.z * w.z + a.w * w.w;
             }
             acc = warp_sum(acc);
-            if (lane == 0) styles[(int64_t)n * rows + r] = (acc * inv + b[r]) * scale[r];
+            if (lane == 0) styles[ooff[r] + (int64_t)n * cin[r]] = (acc * inv + b[r]) * scale[r];
         }
     }
 }
 
-__global__ void __launch_bounds__(256) demod_kernel(const float* __restrict__ styles, int style_rows, const float* __restrict__ wsq,
+// one warp per output channel row r of some layer: styles of that layer at styles[soff[r] + n*cin[r] + i],
+// result at dcoef[ooff[r] + n*cout[r]] (dense [N, Cout] block per layer)
+__global__ void __launch_bounds__(256) demod_kernel(const float* __restrict__ styles, const float* __restrict__ wsq,
                                                     const int64_t* __restrict__ woff, const int* __restrict__ cin,
-                                                    const int* __restrict__ soff, float* __restrict__ dcoef, int rows, int N) {
+                                                    const int64_t* __restrict__ soff, const int64_t* __restrict__ ooff,
+                                                    const int* __restrict__ cout, float* __restrict__ dcoef, int rows, int N) {
     const int lane = threadIdx.x & 31;
     const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t r = warp_global; r < rows; r += nwarps) {
         const float* w = wsq + woff[r];
-        const int c = cin[r], so = soff[r];
+        const int c = cin[r];
         for (int n = 0; n < N; ++n) {
-            const float* s = styles + (int64_t)n * style_rows + so;
+            const float* s = styles + soff[r] + (int64_t)n * c;
             float acc = 0.f;
             for (int i = lane; i < c; i += 32) { const float sv = s[i]; acc += sv * sv * __ldg(w + i); }
             acc = warp_sum(acc);
-            if (lane == 0) dcoef[(int64_t)n * rows + r] = rsqrtf(acc + 1e-8f);
+            if (lane == 0) dcoef[ooff[r] + (int64_t)n * cout[r]] = rsqrtf(acc + 1e-8f);
         }
     }
 }
@@ -91,7 +96,7 @@ __global__ void __launch_bounds__(256) modulate_split_kernel(const float* __rest
 __device__ __constant__ float kFir1[4] = {0.125f, 0.375f, 0.375f, 0.125f};   // immutable constants (not runtime state)
 
 struct EpiParams {
-    const float* dcoef; const float* bias; const float* noise;
+    const float* dcoef; const float* bias; const float* noise; int64_t noise_nstride;
     float gain, slope, clamp;
     N3DSplitOut out[2];
     float* out_f32; int f32_cstride, f32_coff;
@@ -123,7 +128,7 @@ __global__ void __launch_bounds__(256) fir_up_epilogue_kernel(const float* __res
         }
         float v[4] = {acc.x, acc.y, acc.z, acc.w};
         const int c0 = c4 * 4;
-        const float nz = E.noise ? __ldg(E.noise + (int64_t)y * W2 + x) : 0.f;
+        const float nz = E.noise ? __ldg(E.noise + (int64_t)n * E.noise_nstride + (int64_t)y * W2 + x) : 0.f;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float a = v[j];
@@ -192,7 +197,7 @@ __global__ void __launch_bounds__(256) fir_down_split_kernel(const float* __rest
 }
 
 // upsample2d: zero-insert x2, pad (2,1), 4x4 FIR * 4  ->  out[y,x] = sum over input taps with matching parity
-__global__ void __launch_bounds__(256) upsample2d_kernel(const float* __restrict__ x, int N, int H, int W, int C, float* __restrict__ y) {
+__global__ void __launch_bounds__(256) upsample2d_kernel(const float* __restrict__ x, int N, int H, int W, int C, float* __restrict__ y, int nchw) {
     const int OH = 2 * H, OW = 2 * W;
     const int64_t total = (int64_t)N * OH * OW * C;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -213,7 +218,8 @@ __global__ void __launch_bounds__(256) upsample2d_kernel(const float* __restrict
                 acc += (kFir1[fy] * kFir1[fx]) * 4.f * __ldg(x + (((int64_t)n * H + (uy >> 1)) * W + (ux >> 1)) * C + c);
             }
         }
-        y[i] = acc;
+        if (nchw) y[(((int64_t)n * C + c) * OH + oy) * OW + ox] = acc;
+        else y[i] = acc;
     }
 }
 
@@ -245,20 +251,22 @@ __global__ void __launch_bounds__(256) downsample2d_kernel(const float* __restri
 }  // namespace
 
 extern "C" int n3d_styles(const float* ws, int N, int num_ws, int wdim, const float* affine_w, const float* affine_b,
-                          const int32_t* row_widx, const float* row_scale, float* styles, int rows, void* stream) {
-    N3D_CHECK_ARG(ws && affine_w && affine_b && row_widx && row_scale && styles, "n3d_styles: null pointer");
+                          const int32_t* row_widx, const float* row_scale, const int64_t* row_ooff, const int32_t* row_cin,
+                          float* styles, int rows, void* stream) {
+    N3D_CHECK_ARG(ws && affine_w && affine_b && row_widx && row_scale && row_ooff && row_cin && styles, "n3d_styles: null pointer");
     N3D_CHECK_ARG(wdim % 4 == 0 && rows > 0 && N > 0, "n3d_styles: bad sizes");
     styles_kernel<<<grid_for((int64_t)rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(ws, N, num_ws, wdim, affine_w, affine_b, row_widx,
-                                                                                      row_scale, styles, rows);
+                                                                                      row_scale, row_ooff, row_cin, styles, rows);
     N3D_CHECK_LAUNCH("n3d_styles");
     return N3D_OK;
 }
 
-extern "C" int n3d_demod(const float* styles, int style_rows, const float* wsq, const int64_t* row_woff, const int32_t* row_cin,
-                         const int32_t* row_soff, float* dcoef, int rows, int N, void* stream) {
-    N3D_CHECK_ARG(styles && wsq && row_woff && row_cin && row_soff && dcoef, "n3d_demod: null pointer");
-    demod_kernel<<<grid_for((int64_t)rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(styles, style_rows, wsq, row_woff, row_cin, row_soff,
-                                                                                     dcoef, rows, N);
+extern "C" int n3d_demod(const float* styles, const float* wsq, const int64_t* row_woff, const int32_t* row_cin,
+                         const int64_t* row_soff, const int64_t* row_ooff, const int32_t* row_cout, float* dcoef, int rows, int N,
+                         void* stream) {
+    N3D_CHECK_ARG(styles && wsq && row_woff && row_cin && row_soff && row_ooff && row_cout && dcoef, "n3d_demod: null pointer");
+    demod_kernel<<<grid_for((int64_t)rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(styles, wsq, row_woff, row_cin, row_soff, row_ooff,
+                                                                                     row_cout, dcoef, rows, N);
     N3D_CHECK_LAUNCH("n3d_demod");
     return N3D_OK;
 }
@@ -275,12 +283,12 @@ extern "C" int n3d_modulate_split(const float* x, int64_t npix_per_img, int N, i
 }
 
 extern "C" int n3d_fir_up_epilogue(const float* raw, int N, int H2, int W2, int C, const float* dcoef, const float* bias,
-                                   const float* noise, float gain, float slope, float clamp, const N3DSplitOut out[2],
-                                   float* out_f32, int f32_cstride, int f32_coff, void* stream) {
+                                   const float* noise, int64_t noise_nstride, float gain, float slope, float clamp,
+                                   const N3DSplitOut out[2], float* out_f32, int f32_cstride, int f32_coff, void* stream) {
     N3D_CHECK_ARG(raw && out, "n3d_fir_up_epilogue: null pointer");
     N3D_CHECK_ARG(C % 4 == 0, "n3d_fir_up_epilogue: C must be a multiple of 4");
     EpiParams E;
-    E.dcoef = dcoef; E.bias = bias; E.noise = noise; E.gain = gain; E.slope = slope; E.clamp = clamp;
+    E.dcoef = dcoef; E.bias = bias; E.noise = noise; E.noise_nstride = noise_nstride; E.gain = gain; E.slope = slope; E.clamp = clamp;
     E.out[0] = out[0]; E.out[1] = out[1]; E.out_f32 = out_f32; E.f32_cstride = f32_cstride; E.f32_coff = f32_coff;
     for (int k = 0; k < 2; ++k)
         N3D_CHECK_ARG(!E.out[k].hi || ((E.out[k].cstride % 4 == 0) && (E.out[k].coff % 4 == 0)), "n3d_fir_up_epilogue: unaligned split output");
@@ -300,9 +308,9 @@ extern "C" int n3d_fir_down_split(const float* x, int N, int H, int W, int C, vo
     return N3D_OK;
 }
 
-extern "C" int n3d_upsample2d_nhwc(const float* x, int N, int H, int W, int C, float* y, void* stream) {
+extern "C" int n3d_upsample2d_nhwc(const float* x, int N, int H, int W, int C, float* y, int y_nchw, void* stream) {
     N3D_CHECK_ARG(x && y, "n3d_upsample2d_nhwc: null pointer");
-    upsample2d_kernel<<<grid_for((int64_t)N * 4 * H * W * C, 256, 16), 256, 0, (cudaStream_t)stream>>>(x, N, H, W, C, y);
+    upsample2d_kernel<<<grid_for((int64_t)N * 4 * H * W * C, 256, 16), 256, 0, (cudaStream_t)stream>>>(x, N, H, W, C, y, y_nchw);
     N3D_CHECK_LAUNCH("n3d_upsample2d_nhwc");
     return N3D_OK;
 }

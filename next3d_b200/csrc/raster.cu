@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(256) uv_sample_kernel(const int* __restrict__ 
             else if (lane < C) {
                 const int plane = view == 0 ? 0 : (view == 2 ? 1 : 2);
                 const float val = view == 2 ? side_acc + acc : acc;
-                planes[(((int64_t)n * 3 + plane) * H * W + pix) * C + lane] = val;
+                planes[(((int64_t)plane * N + n) * H * W + pix) * C + lane] = val;
             }
             if (view != 2 && lane == 0) {
                 int mx0, my0; float mfx, mfy;
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(256) uv_sample_kernel(const int* __restrict__ 
                     if (mx0 + 1 >= 0 && mx0 + 1 < MW) m += mfx * mfy * __ldg(mask + (my0 + 1) * MW + mx0 + 1);
                 }
                 const int aplane = view == 0 ? 0 : (view == 1 ? 1 : 2);
-                alpha[((int64_t)n * 3 + aplane) * H * W + pix] = m * vis;
+                alpha[((int64_t)aplane * N + n) * H * W + pix] = m * vis;
             }
         }
     }
@@ -350,9 +350,9 @@ __global__ void __launch_bounds__(256) blend_kernel(const float* __restrict__ fr
         const int64_t pix = t % HW; t /= HW;
         const int p = (int)(t % 3);
         const int n = (int)(t / 3);
-        const float a = __ldg(alpha + ((int64_t)n * 3 + p) * HW + pix);
+        const float a = __ldg(alpha + ((int64_t)p * N + n) * HW + pix);
         const float4 tv = p == 0 ? __ldg(reinterpret_cast<const float4*>(front + ((int64_t)n * HW + pix) * 32) + c4)
-                                 : __ldg(reinterpret_cast<const float4*>(tex + (((int64_t)n * 3 + p) * HW + pix) * 32) + c4);
+                                 : __ldg(reinterpret_cast<const float4*>(tex + (((int64_t)p * N + n) * HW + pix) * 32) + c4);
         const float4 sv = __ldg(reinterpret_cast<const float4*>(stat + ((int64_t)n * HW + pix) * 96 + p * 32) + c4);
         const float b = 1.f - a;
         float4 o;

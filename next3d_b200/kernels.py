@@ -53,7 +53,7 @@ def make_split_out(hi=None, lo=None, style=None, cstride=0, coff=0):
 
 # ------------------------------------------------------------------------------------------------ kernels
 def conv_gemm(a_hi, a_lo, w_hi, w_lo, taps, N, MH, MW, *, a_img_mul=0, nprod=3, mode=0, dcoef=None, bias=None, noise=None,
-              gain=1.0, slope=1.0, clamp=-1.0, outs=(), out_f32=None, f32_cstride=0, f32_coff=0, f32_nchw=False,
+              noise_nstride=0, gain=1.0, slope=1.0, clamp=-1.0, outs=(), out_f32=None, f32_cstride=0, f32_coff=0, f32_nchw=False,
               f32_accumulate=False, oy_mul=1, oy_off=0, ox_mul=1, ox_off=0, OH=None, OW=None):
     """a_*: bf16 [NI, AH, AW, Cin]; w_*: bf16 [T, Cout, Cin]; taps: list of (dy, dx, img_off, wtap)."""
     NI, AH, AW, Cin = a_hi.shape
@@ -69,7 +69,7 @@ def conv_gemm(a_hi, a_lo, w_hi, w_lo, taps, N, MH, MW, *, a_img_mul=0, nprod=3, 
     for i, (dy, dx, io, wt) in enumerate(taps):
         p.taps[i] = _lib.ConvTap(dy, dx, io, wt)
     p.nprod, p.mode = nprod, mode
-    p.dcoef, p.bias, p.noise = ptr(dcoef), ptr(bias), ptr(noise)
+    p.dcoef, p.bias, p.noise, p.noise_nstride = ptr(dcoef), ptr(bias), ptr(noise), noise_nstride
     p.gain, p.slope, p.clamp = gain, slope, clamp
     for i, o in enumerate(outs):
         p.out[i] = o
@@ -88,12 +88,12 @@ def modulate_split(x, style, hi, lo, cstride=None, coff=0):
           'n3d_modulate_split')
 
 
-def fir_up_epilogue(raw, C_, dcoef, bias, noise, gain, slope, clamp, outs=(), out_f32=None, f32_cstride=0, f32_coff=0):
+def fir_up_epilogue(raw, C_, dcoef, bias, noise, gain, slope, clamp, outs=(), out_f32=None, f32_cstride=0, f32_coff=0, noise_nstride=0):
     N, RH, RW, _ = raw.shape
     arr = (_lib.SplitOut * 2)()
     for i, o in enumerate(outs):
         arr[i] = o
-    check(lib.n3d_fir_up_epilogue(ptr(raw), N, RH - 1, RW - 1, C_, ptr(dcoef), ptr(bias), ptr(noise), gain, slope, clamp, arr,
+    check(lib.n3d_fir_up_epilogue(ptr(raw), N, RH - 1, RW - 1, C_, ptr(dcoef), ptr(bias), ptr(noise), noise_nstride, gain, slope, clamp, arr,
                                   ptr(out_f32), f32_cstride, f32_coff, stream_ptr()), 'n3d_fir_up_epilogue')
 
 
@@ -102,9 +102,9 @@ def fir_down_split(x, hi, lo):
     check(lib.n3d_fir_down_split(ptr(x), N, H, W, Cc, ptr(hi), ptr(lo), stream_ptr()), 'n3d_fir_down_split')
 
 
-def upsample2d_nhwc(x, y):
+def upsample2d_nhwc(x, y, y_nchw=False):
     N, H, W, Cc = x.shape
-    check(lib.n3d_upsample2d_nhwc(ptr(x), N, H, W, Cc, ptr(y), stream_ptr()), 'n3d_upsample2d_nhwc')
+    check(lib.n3d_upsample2d_nhwc(ptr(x), N, H, W, Cc, ptr(y), int(y_nchw), stream_ptr()), 'n3d_upsample2d_nhwc')
 
 
 def downsample2d_nhwc(x, y):
@@ -112,18 +112,18 @@ def downsample2d_nhwc(x, y):
     check(lib.n3d_downsample2d_nhwc(ptr(x), N, H, W, Cc, ptr(y), stream_ptr()), 'n3d_downsample2d_nhwc')
 
 
-def styles(ws, affine_w, affine_b, row_widx, row_scale, out):
+def styles(ws, affine_w, affine_b, row_widx, row_scale, row_ooff, row_cin, out):
+    """out: flat fp32; layer blocks are dense [N, Cin] at row_ooff (see include/next3d_b200.h)."""
     N, num_ws, wdim = ws.shape
     rows = affine_w.shape[0]
-    check(lib.n3d_styles(ptr(ws), N, num_ws, wdim, ptr(affine_w), ptr(affine_b), ptr(row_widx), ptr(row_scale), ptr(out), rows,
-                         stream_ptr()), 'n3d_styles')
+    check(lib.n3d_styles(ptr(ws), N, num_ws, wdim, ptr(affine_w), ptr(affine_b), ptr(row_widx), ptr(row_scale), ptr(row_ooff),
+                         ptr(row_cin), ptr(out), rows, stream_ptr()), 'n3d_styles')
 
 
-def demod(styles_t, wsq, row_woff, row_cin, row_soff, out):
-    N, style_rows = styles_t.shape
+def demod(styles_flat, wsq, row_woff, row_cin, row_soff, row_ooff, row_cout, out, N):
     rows = row_cin.shape[0]
-    check(lib.n3d_demod(ptr(styles_t), style_rows, ptr(wsq), ptr(row_woff), ptr(row_cin), ptr(row_soff), ptr(out), rows, N,
-                        stream_ptr()), 'n3d_demod')
+    check(lib.n3d_demod(ptr(styles_flat), ptr(wsq), ptr(row_woff), ptr(row_cin), ptr(row_soff), ptr(row_ooff), ptr(row_cout),
+                        ptr(out), rows, N, stream_ptr()), 'n3d_demod')
 
 
 def transform_points(pts, rot, zoff, ndc_flip, out):
