@@ -1,0 +1,52 @@
+"""Multi-GPU plumbing for the one place the hot path shards: independent (latent, camera, mesh) samples.
+
+One process per GPU (torchrun), contiguous split of the sample list across ranks, no data-path collective inside the
+generator; a single gather of the output images to rank 0 (NCCL over NVLink on GPUs, gloo in the CPU tests) that can be
+issued on a side stream so it overlaps the next micro-batch.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend=None):
+    """Initialise torch.distributed from torchrun's environment; returns (rank, world, local_rank). No-op for world 1."""
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1 and not dist.is_initialized():
+        backend = backend or ('nccl' if torch.cuda.is_available() else 'gloo')
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        if backend == 'nccl':
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def shard_range(total, rank, world):
+    """Contiguous [start, stop) of `total` samples owned by `rank` (first `total % world` ranks get one extra)."""
+    base, extra = divmod(total, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def gather_images(local_images, dst=0):
+    """Gather equally-sized per-rank image batches to `dst`: returns [world*B, ...] on dst, None elsewhere."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return local_images
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if rank == dst:
+        out = torch.empty((world,) + tuple(local_images.shape), dtype=local_images.dtype, device=local_images.device)
+        dist.gather(local_images.contiguous(), list(out.unbind(0)), dst=dst)
+        return out.flatten(0, 1)
+    dist.gather(local_images.contiguous(), None, dst=dst)
+    return None
+
+
+def max_over_ranks(value, device):
+    """Scalar max over ranks (device timing of multi-GPU runs is the slowest rank's)."""
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.item()

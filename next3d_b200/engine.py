@@ -72,6 +72,8 @@ class Engine:
         self.rk = cfg.rendering_kwargs
         self.mod, self.plain = {}, {}
         self.launches = 0
+        self.conv_flops = 0.0
+        self.prof = None
         sd = {k: v.to(self.device, non_blocking=True) if isinstance(v, torch.Tensor) else v for k, v in state_dict.items()}
         self._pack(sd)
         self._tables = {}
@@ -198,6 +200,38 @@ class Engine:
             t = self._tables[N] = (s_ooff, d_soff, d_ooff)
         return t
 
+    # ------------------------------------------------------------------------------------------ instrumentation
+    def _prof_begin(self):
+        if self.prof is None:
+            return None
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        return e0
+
+    def _prof_end(self, e0, kind, flops=0):
+        if e0 is None:
+            return
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        self.prof.append((kind, e0, e1, flops))
+
+    def _gemm(self, a_hi, a_lo, w_hi, w_lo, taps, N, MH, MW, **kw):
+        """n3d_conv_gemm + bookkeeping: algorithmic FLOPs = 2 * Cin * Cout * taps * M-space positions (one product)."""
+        flops = 2.0 * a_hi.shape[-1] * w_hi.shape[1] * len(taps) * N * MH * MW
+        self.conv_flops += flops
+        ev = self._prof_begin()
+        K.conv_gemm(a_hi, a_lo, w_hi, w_lo, taps, N, MH, MW, **kw)
+        self._prof_end(ev, 'conv_gemm', flops)
+
+    def profile_summary(self):
+        """After a synthesis() with self.prof = []: {kind: (launches, total_ms, total_flops)} (synchronises)."""
+        torch.cuda.synchronize(self.device)
+        out = {}
+        for kind, e0, e1, fl in self.prof or []:
+            n, ms, f = out.get(kind, (0, 0.0, 0.0))
+            out[kind] = (n + 1, ms + e0.elapsed_time(e1), f + fl)
+        return out
+
     # ------------------------------------------------------------------------------------------ small helpers
     def _style(self, L):
         return self._styles[L.sbase * self._N: (L.sbase + L.cin) * self._N]
@@ -228,7 +262,7 @@ class Engine:
         noise, nstride = self._noise(L, noise_mode)
         clamp = L.clamp if L.clamp is not None else -1.0
         if L.up == 1:
-            K.conv_gemm(a.hi, a.lo, L.w_hi, L.w_lo, K.taps_conv3x3(), N, res_in, res_in, nprod=self.nprod, dcoef=self._dcoef(L), bias=L.bias,
+            self._gemm(a.hi, a.lo, L.w_hi, L.w_lo, K.taps_conv3x3(), N, res_in, res_in, nprod=self.nprod, dcoef=self._dcoef(L), bias=L.bias,
                         noise=noise, noise_nstride=nstride, gain=SQRT2, slope=0.2, clamp=clamp, outs=outs, out_f32=f32,
                         f32_cstride=L.cout if f32 is not None else 0)
             self.launches += 1
@@ -236,7 +270,7 @@ class Engine:
         raw = self._f32(N, 2 * res_in + 1, 2 * res_in + 1, L.cout)
         for pa in (0, 1):
             for pb in (0, 1):
-                K.conv_gemm(a.hi, a.lo, L.w_hi, L.w_lo, K.taps_transposed(pa, pb), N, res_in + 1 - pa, res_in + 1 - pb, nprod=self.nprod,
+                self._gemm(a.hi, a.lo, L.w_hi, L.w_lo, K.taps_transposed(pa, pb), N, res_in + 1 - pa, res_in + 1 - pb, nprod=self.nprod,
                             mode=1, out_f32=raw, f32_cstride=L.cout, oy_mul=2, oy_off=pa, ox_mul=2, ox_off=pb, OH=2 * res_in + 1,
                             OW=2 * res_in + 1)
         K.fir_up_epilogue(raw, L.cout, self._dcoef(L), L.bias, noise, SQRT2, 0.2, clamp, outs=outs, out_f32=f32,
@@ -246,7 +280,7 @@ class Engine:
     def _torgb(self, name, a, res, img, accumulate, nchw=False):
         """ToRGBLayer (networks_stylegan2.py:353-357): 1x1 modulated conv without demodulation, linear bias (+ clamp)."""
         L = self.mod[name]
-        K.conv_gemm(a.hi, a.lo, L.w_hi, L.w_lo, K.taps_conv1x1(), self._N, res, res, nprod=self.nprod, bias=L.bias,
+        self._gemm(a.hi, a.lo, L.w_hi, L.w_lo, K.taps_conv1x1(), self._N, res, res, nprod=self.nprod, bias=L.bias,
                     clamp=L.clamp if L.clamp is not None else -1.0, out_f32=img, f32_cstride=L.cout, f32_nchw=nchw, f32_accumulate=accumulate)
         self.launches += 1
 
@@ -255,11 +289,11 @@ class Engine:
         L, N = self.plain[name], self._N
         gain, slope = (SQRT2, 0.2) if act == 'lrelu' else (1.0, 1.0)
         if stride2:
-            K.conv_gemm(a.hi, a.lo, L.w_hi, L.w_lo, K.taps_stride2(), N, res // 2, res // 2, a_img_mul=N, nprod=self.nprod, bias=L.bias, gain=gain,
+            self._gemm(a.hi, a.lo, L.w_hi, L.w_lo, K.taps_stride2(), N, res // 2, res // 2, a_img_mul=N, nprod=self.nprod, bias=L.bias, gain=gain,
                         slope=slope, outs=outs, out_f32=f32, f32_cstride=L.cout if f32 is not None else 0, f32_accumulate=accumulate)
         else:
             taps = K.taps_conv3x3() if L.k == 3 else K.taps_conv1x1()
-            K.conv_gemm(a.hi, a.lo, L.w_hi, L.w_lo, taps, N, res, res, nprod=self.nprod, bias=L.bias, gain=gain, slope=slope, outs=outs,
+            self._gemm(a.hi, a.lo, L.w_hi, L.w_lo, taps, N, res, res, nprod=self.nprod, bias=L.bias, gain=gain, slope=slope, outs=outs,
                         out_f32=f32, f32_cstride=L.cout if f32 is not None else 0, f32_accumulate=accumulate)
         self.launches += 1
 
@@ -487,6 +521,7 @@ class Engine:
         N = ws.shape[0]
         R = neural_rendering_resolution or cfg.neural_rendering_resolution
         self.launches = 0
+        self.conv_flops = 0.0
         out = self.compute_planes(ws, v, noise_mode, return_intermediates)
         planes, inter = out if return_intermediates else (out, None)
         c = c.to(torch.float32)
@@ -500,7 +535,9 @@ class Engine:
         u_c, u_f = sampler_noise if sampler_noise is not None else (None, None)
         if u_c is not None:
             u_c, u_f = u_c.to(dev, torch.float32).contiguous(), u_f.to(dev, torch.float32).contiguous()
+        ev = self._prof_begin()
         K.render_rays(planes, cam, intr, R, self.rk, self.dec, feat, depth, wsum, mm, u_coarse=u_c, u_fine=u_f, seed=seed)
+        self._prof_end(ev, 'render_rays')
         K.depth_clamp(depth, mm)
         image = self._f32(N, 3, cfg.img_resolution, cfg.img_resolution)
         self._superresolution(feat, self.rk['superresolution_noise_mode'], image)
