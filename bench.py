@@ -149,6 +149,7 @@ def run_ours(args):
     cfg = config.full_config(512)
     sd = weights.make_state_dict(cfg, seed=0)
     G = TriPlaneGenerator.from_config(cfg, sd, device=dev)
+    G.use_cuda_graph = not args.no_graph
     del sd
     # global sample ids: rank r owns [r*B, (r+1)*B)
     z, c_cond, c_cam, v = weights.demo_inputs(cfg, B * world, seed=0)
@@ -162,6 +163,8 @@ def run_ours(args):
     side = torch.cuda.Stream(dev)
 
     def step_device(i):
+        if world > 1:                                   # the static graph outputs must not be overwritten while the gather reads them
+            torch.cuda.current_stream(dev).wait_stream(side)
         out = G.synthesis(ws_d, c_d, v_d, noise_mode='const', seed=1000 + i)
         if world > 1:                                   # the one collective of the path: gather the images on rank 0
             side.wait_stream(torch.cuda.current_stream(dev))
@@ -223,6 +226,7 @@ def run_ours(args):
         roof = roof_r = None
         if rank == 0:
             eng.prof = []
+            G.use_cuda_graph = False                         # events around every launch need the eager path
             G.synthesis(ws_d, c_d, v_d, noise_mode='const', seed=5)
             summ = eng.profile_summary()
             eng.prof = None
@@ -251,6 +255,7 @@ def run_ours(args):
         'dtype': 'bf16x3 (hi/lo split operands, fp32 accumulate) for convs; f32 elsewhere', 'data': 'synthetic',
         'config': {'workload': 'FFHQ-512 generator forward (TriPlaneGenerator.synthesis): 64^2 neural render -> 512^2 SR, 48+48 depth samples, '
                                f'batch {B} per GPU', 'global_batch': B * world, 'parallelism': f'batch-sharded x{world}, one gather of images',
+                   'launch': 'eager' if args.no_graph else 'one CUDA graph replay per step',
                    'l2': 'no explicit flush: per-step working set (0.7 GB packed weights + >4 GB activations) >> 126 MB L2'},
         'clocks': clocks,
         'e2e': {'value': imgs / dt_e2e, 'unit': UNIT, 'h2d_bytes_per_step': int(ws_host.numel() * 4 + c_host.numel() * 4 + v_host.numel() * 4),
@@ -273,6 +278,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=8, help='samples per GPU per step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='launch kernels eagerly instead of replaying the captured CUDA graph')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     if args.impl == 'reference':

@@ -214,6 +214,7 @@ typedef struct {
     const float* u_coarse;     /* [N, M, Dc] injected uniforms or NULL (= in-kernel counter RNG with `seed`) */
     const float* u_fine;       /* [N*M, Df] or NULL */
     uint64_t seed;
+    const uint64_t* seed_ptr;  /* optional device counter added to `seed` (lets a captured CUDA graph draw fresh noise per replay) */
     const float* w0; const float* b0;   /* decoder.net.0: [64,32] (already * 1/sqrt(32)), [64] */
     const float* w1; const float* b1;   /* decoder.net.2: [33,64] (already * 1/sqrt(64)), [33] */
     float* rgb;                /* [N, M, 32] */

@@ -8,7 +8,8 @@
 // v1 organisation (SIMT fp32, exact-math transcendental functions):
 //   CTA = RAYS rays x D samples = up to 192 threads.  Gather: one warp per sample, lanes = the 32 channels, so each of the
 //   12 bilinear taps is one coalesced 128-byte line of the channels-last planes.  Decode: one thread per sample, weights
-//   broadcast from shared memory as float4.  Per-ray scans (weights, CDF inversion, merge) run one thread per ray.
+//   broadcast from shared memory as float4.  Per-ray work (compositing weights via a warp product scan, CDF build + inversion,
+//   rank-counting sort-merge, colour accumulation) runs one warp per ray.
 #include "common.cuh"
 #include "../../include/next3d_b200.h"
 
@@ -119,23 +120,40 @@ __device__ __forceinline__ void load_decoder(const float* w0, const float* b0, c
     for (int i = threadIdx.x; i < kW1Stride; i += blockDim.x) sB1[i] = i < kOut ? b1[i] : 0.f;
 }
 
-// MipRayMarcher2 weights for one sorted sample list (thread-sequential): w[k], k < cnt-1.  Returns sum of weights.
-template <typename DepthAt, typename SigmaAt>
-__device__ __forceinline__ float march_weights(int cnt, DepthAt depth_at, SigmaAt sigma_at, float* w) {
-    float T = 1.f, wsum = 0.f;
-    float t_prev = depth_at(0), s_prev = sigma_at(0);
-    for (int k = 0; k < cnt - 1; ++k) {
-        const float t_next = depth_at(k + 1), s_next = sigma_at(k + 1);
-        const float delta = t_next - t_prev;
-        const float dens = softplus_t((s_prev + s_next) / 2.f - 1.f);
-        const float alpha = 1.f - expf(-(dens * delta));
-        const float wk = alpha * T;
-        w[k] = wk;
-        wsum += wk;
-        T *= (1.f - alpha + 1e-10f);
-        t_prev = t_next; s_prev = s_next;
+// ---- warp-cooperative per-ray primitives (one warp owns one ray; lanes stride over the samples) ----
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// MipRayMarcher2 weights (ray_marcher.py:27-46) of a depth-sorted sample list held in shared memory:
+//   alpha_k = 1 - exp(-softplus((s_k + s_k+1)/2 - 1) * (t_k+1 - t_k)),  T_k = prod_{i<k} (1 - alpha_i + 1e-10),  w_k = alpha_k T_k
+// computed by the whole warp: alphas in parallel, the transmittance by a chunked warp product scan.  Returns sum_k w_k.
+__device__ __forceinline__ float warp_march_weights(int cnt, const float* __restrict__ t, const float* __restrict__ sg, float* __restrict__ w, int lane) {
+    float carry = 1.f, wsum = 0.f;
+    for (int base = 0; base < cnt - 1; base += 32) {
+        const int k = base + lane;
+        float alpha = 0.f;
+        if (k < cnt - 1) {
+            const float delta = t[k + 1] - t[k];
+            const float dens = softplus_t((sg[k] + sg[k + 1]) / 2.f - 1.f);
+            alpha = 1.f - expf(-(dens * delta));
+        }
+        float f = k < cnt - 1 ? (1.f - alpha + 1e-10f) : 1.f;
+        float inc = f;                                   // inclusive product scan over the 32 lanes
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float up = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc *= up;
+        }
+        float exc = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) exc = 1.f;
+        const float T = carry * exc;
+        if (k < cnt - 1) { const float wk = alpha * T; w[k] = wk; wsum += wk; }
+        carry *= __shfl_sync(0xffffffffu, inc, 31);
     }
-    return wsum;
+    return warp_sum_f(wsum);
 }
 
 __global__ void __launch_bounds__(kMaxThreads) render_kernel(const RenderK K) {
@@ -153,11 +171,13 @@ __global__ void __launch_bounds__(kMaxThreads) render_kernel(const RenderK K) {
     float* sTc = sF + R * Df * kRowStride;               // coarse depths [R][Dc]
     float* sTf = sTc + R * Dc;                           // fine depths   [R][Df]
     float* sWgt = sTf + R * Df;                          // weights [R][Dt]
-    float* sRay = sWgt + R * Dt;                         // [R][8]: origin xyz, dir xyz
+    float* sScr = sWgt + R * Dt;                         // per-ray scratch [R][3*Dt]: sorted depths | sorted sigmas | cdf
+    float* sRay = sScr + R * 3 * Dt;                     // [R][8]: origin xyz, dir xyz
     unsigned char* sOrd = reinterpret_cast<unsigned char*>(sRay + R * 8);   // [R][Dt] merged order
     __shared__ float s_min[kMaxThreads / 32], s_max[kMaxThreads / 32];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const uint64_t seed = P.seed_ptr ? (P.seed + __ldg(reinterpret_cast<const unsigned long long*>(P.seed_ptr))) : P.seed;
     const int64_t ray0 = (int64_t)blockIdx.x * R;        // global ray index = n*M + m
     const int64_t total_rays = (int64_t)P.N * K.M;
 
@@ -195,7 +215,7 @@ __global__ void __launch_bounds__(kMaxThreads) render_kernel(const RenderK K) {
         const int64_t gr = ray0 + r;
         float t = 0.f;
         if (gr < total_rays) {
-            const float u = P.u_coarse ? __ldg(P.u_coarse + gr * Dc + k) : hash_uniform(P.seed, (uint64_t)(gr * Dc + k));
+            const float u = P.u_coarse ? __ldg(P.u_coarse + gr * Dc + k) : hash_uniform(seed, (uint64_t)(gr * Dc + k));
             t = linspace_at(P.ray_start, P.ray_end, Dc, k) + u * K.delta_coarse;
         }
         sTc[s] = t;
@@ -221,32 +241,49 @@ __global__ void __launch_bounds__(kMaxThreads) render_kernel(const RenderK K) {
     for (int s = tid; s < R * Dc; s += blockDim.x) decode_row(sC + s * kRowStride, sW0, sB0, sW1t, sB1);
     __syncthreads();
 
-    // ---- per ray: coarse weights -> smoothed pdf -> inverse-CDF samples (renderer.py:209-268)
-    if (tid < R && ray0 + tid < total_rays && Df > 0) {
-        const int r = tid;
+    // ---- per ray (one warp each): coarse weights -> smoothed pdf -> inverse-CDF samples (renderer.py:209-268)
+    for (int r = warp; r < R; r += nwarps) {
         const int64_t gr = ray0 + r;
-        float* w = sWgt + r * Dt;               // scratch: weights [Dc-1], then pdf/cdf
+        if (gr >= total_rays || Df <= 0) continue;
+        float* w = sWgt + r * Dt;                // weights [Dc-1]
+        float* sg = sScr + r * 3 * Dt;           // coarse sigmas gathered contiguously
+        float* cdf = sg + 2 * Dt;                // [nw+1]
         const float* tc = sTc + r * Dc;
         const float* rows = sC + (r * Dc) * kRowStride;
-        march_weights(Dc, [&](int k) { return tc[k]; }, [&](int k) { return rows[k * kRowStride + 32]; }, w);
+        for (int k = lane; k < Dc; k += 32) sg[k] = rows[k * kRowStride + 32];
+        __syncwarp();
+        warp_march_weights(Dc, tc, sg, w, lane);
+        __syncwarp();
         // max_pool1d(k2,s1,pad1) -> avg_pool1d(k2,s1) -> +0.01 ; keep entries [1:-1] => Dc-3 pdf weights, + 1e-5
         const int nw = Dc - 3;
-        float* cdf = w + Dc;                     // [nw+1] (Dt - Dc = Df >= nw + 1 is checked on the host)
-        float total = 0.f;
-        for (int i = 0; i < nw; ++i) {
-            const int q = i + 1;                 // index into the avg-pooled array (length Dc-1)
-            const float mp0 = fmaxf(w[q - 1], w[q]);                                   // maxpool[q]   = max(w[q-1], w[q])
-            const float mp1 = q + 1 <= Dc - 2 ? fmaxf(w[q], w[q + 1]) : w[q];          // maxpool[q+1] = max(w[q], w[q+1]) (last: w[Dc-2])
+        float part = 0.f;
+        for (int i = lane; i < nw; i += 32) {
+            const int q = i + 1;
+            const float mp0 = fmaxf(w[q - 1], w[q]);
+            const float mp1 = q + 1 <= Dc - 2 ? fmaxf(w[q], w[q + 1]) : w[q];
             const float v = (mp0 + mp1) * 0.5f + 0.01f + 1e-5f;
             cdf[i + 1] = v;
-            total += v;
+            part += v;
         }
-        cdf[0] = 0.f;
-        float run = 0.f;
-        for (int i = 0; i < nw; ++i) { run += cdf[i + 1] / total; cdf[i + 1] = run; }
+        const float total = warp_sum_f(part);
+        __syncwarp();
+        float carry = 0.f;                       // inclusive sum scan of pdf = v / total
+        for (int base = 0; base < nw; base += 32) {
+            const int i = base + lane;
+            float inc = i < nw ? cdf[i + 1] / total : 0.f;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const float up = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += up;
+            }
+            if (i < nw) cdf[i + 1] = carry + inc;
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) cdf[0] = 0.f;
+        __syncwarp();
         float* tf = sTf + r * Df;
-        for (int j = 0; j < Df; ++j) {
-            const float u = P.u_fine ? __ldg(P.u_fine + gr * Df + j) : hash_uniform(P.seed ^ 0xA5A5A5A5DEADBEEFull, (uint64_t)(gr * Df + j));
+        for (int j = lane; j < Df; j += 32) {
+            const float u = P.u_fine ? __ldg(P.u_fine + gr * Df + j) : hash_uniform(seed ^ 0xA5A5A5A5DEADBEEFull, (uint64_t)(gr * Df + j));
             int lo = 0, hi = nw + 1;             // searchsorted(cdf, u, right=True): first index with cdf[idx] > u
             while (lo < hi) { const int mid = (lo + hi) >> 1; if (cdf[mid] <= u) lo = mid + 1; else hi = mid; }
             const int below = max(lo - 1, 0), above = min(lo, nw);
@@ -275,67 +312,61 @@ __global__ void __launch_bounds__(kMaxThreads) render_kernel(const RenderK K) {
     for (int s = tid; s < R * Df; s += blockDim.x) decode_row(sF + s * kRowStride, sW0, sB0, sW1t, sB1);
     __syncthreads();
 
-    // ---- per ray: stable sort-merge of coarse (already sorted) and fine depths, final weights (renderer.py:164-182)
+    // ---- per ray (one warp each): stable sort-merge of coarse (already sorted) and fine depths by rank counting
+    //      (torch.sort on the concatenation, renderer.py:164-182: ties keep coarse before fine and fine in input order),
+    //      final weights, composite depth and colours (ray_marcher.py:27-66)
     float dmin = INFINITY, dmax = -INFINITY;
-    if (tid < R && ray0 + tid < total_rays) {
-        const int r = tid;
-        const float* tc = sTc + r * Dc;
-        const float* tf = sTf + r * Df;
-        unsigned char* ord = sOrd + r * Dt;
-        // insertion sort of fine indices by depth (stable), kept in the tail of `ord`
-        unsigned char* fo = ord + Dc;
-        for (int j = 0; j < Df; ++j) {
-            const float v = tf[j];
-            int q = j;
-            while (q > 0 && tf[fo[q - 1]] > v) { fo[q] = fo[q - 1]; --q; }
-            fo[q] = (unsigned char)j;
-        }
-        // merge: on ties the coarse sample comes first (it precedes the fine ones in the concatenated tensor)
-        int a = 0, b = 0;
-        unsigned char tmp[2 * kMaxD];
-        for (int k = 0; k < Dt; ++k) {
-            const bool take_c = b >= Df || (a < Dc && tc[a] <= tf[fo[b]]);
-            tmp[k] = take_c ? (unsigned char)(a++) : (unsigned char)(Dc + fo[b++]);
-        }
-        for (int k = 0; k < Dt; ++k) ord[k] = tmp[k];
-        const float* rc = sC + (r * Dc) * kRowStride;
-        const float* rf = sF + (r * Df) * kRowStride;
-        auto depth_at = [&](int k) { const int o = ord[k]; return o < Dc ? tc[o] : tf[o - Dc]; };
-        auto sigma_at = [&](int k) { const int o = ord[k]; return o < Dc ? rc[o * kRowStride + 32] : rf[(o - Dc) * kRowStride + 32]; };
-        float* w = sWgt + r * Dt;
-        const float wsum = march_weights(Dt, depth_at, sigma_at, w);
-        float dacc = 0.f;
-        for (int k = 0; k < Dt - 1; ++k) dacc += w[k] * ((depth_at(k) + depth_at(k + 1)) / 2.f);
-        float depth = dacc / wsum;
-        if (isnan(depth)) depth = INFINITY;                         // nan_to_num(nan=inf); the clamp kernel finishes the job
-        const int64_t gr = ray0 + r;
-        P.depth[gr] = depth;
-        P.wsum[gr] = wsum;
-        dmin = fminf(depth_at(0), dmin);
-        dmax = fmaxf(depth_at(Dt - 1), dmax);
-    }
-    __syncthreads();
-
-    // ---- composite colours: warp per ray, lanes = channels
     for (int r = warp; r < R; r += nwarps) {
         const int64_t gr = ray0 + r;
         if (gr >= total_rays) continue;
-        const unsigned char* ord = sOrd + r * Dt;
-        const float* w = sWgt + r * Dt;
+        const float* tc = sTc + r * Dc;
+        const float* tf = sTf + r * Df;
         const float* rc = sC + (r * Dc) * kRowStride;
         const float* rf = sF + (r * Df) * kRowStride;
+        unsigned char* ord = sOrd + r * Dt;
+        float* sd = sScr + r * 3 * Dt;           // sorted depths
+        float* sg = sd + Dt;                     // sorted sigmas
+        float* w = sWgt + r * Dt;
+        for (int a = lane; a < Dc; a += 32) {    // coarse sample a lands after every strictly smaller fine sample
+            const float v = tc[a];
+            int pos = a;
+            for (int i = 0; i < Df; ++i) pos += tf[i] < v ? 1 : 0;
+            ord[pos] = (unsigned char)a; sd[pos] = v; sg[pos] = rc[a * kRowStride + 32];
+        }
+        for (int j = lane; j < Df; j += 32) {    // fine sample j: rank among the fine ones (stable) + coarse samples <= it
+            const float v = tf[j];
+            int pos = 0;
+            for (int i = 0; i < Df; ++i) pos += (tf[i] < v || (tf[i] == v && i < j)) ? 1 : 0;
+            for (int a = 0; a < Dc; ++a) pos += tc[a] <= v ? 1 : 0;
+            ord[pos] = (unsigned char)(Dc + j); sd[pos] = v; sg[pos] = rf[j * kRowStride + 32];
+        }
+        __syncwarp();
+        const float wsum = warp_march_weights(Dt, sd, sg, w, lane);
+        __syncwarp();
+        float dacc = 0.f;
+        for (int k = lane; k < Dt - 1; k += 32) dacc += w[k] * ((sd[k] + sd[k + 1]) / 2.f);
+        dacc = warp_sum_f(dacc);
+        if (lane == 0) {
+            float depth = dacc / wsum;
+            if (isnan(depth)) depth = INFINITY;                     // nan_to_num(nan=inf); the clamp kernel finishes the job
+            P.depth[gr] = depth;
+            P.wsum[gr] = wsum;
+            dmin = fminf(sd[0], dmin);
+            dmax = fmaxf(sd[Dt - 1], dmax);
+        }
+        // colours: lanes = channels
         auto color_at = [&](int k) { const int o = ord[k]; return o < Dc ? rc[o * kRowStride + lane] : rf[(o - Dc) * kRowStride + lane]; };
-        float acc = 0.f, wtot = 0.f;
+        float acc = 0.f;
         float c_prev = color_at(0);
         for (int k = 0; k < Dt - 1; ++k) {
             const float c_next = color_at(k + 1);
             acc += w[k] * ((c_prev + c_next) / 2.f);
-            wtot += w[k];
             c_prev = c_next;
         }
-        if (P.white_back) acc = acc + 1.f - wtot;
+        if (P.white_back) acc = acc + 1.f - wsum;
         P.rgb[gr * kFeat + lane] = acc * 2.f - 1.f;
     }
+    __syncthreads();
 
     // ---- batch-global depth range (ray_marcher.py:54): warp + block reduce, then one atomic pair per CTA
 #pragma unroll
@@ -404,7 +435,7 @@ __global__ void __launch_bounds__(kMaxThreads) sample_points_kernel(const float*
 size_t render_smem_bytes(int R, int Dc, int Df) {
     const int Dt = Dc + Df;
     size_t fl = (size_t)kHidden * kFeat + kHidden * kW1Stride + kHidden + kW1Stride + (size_t)R * Dc * kRowStride + (size_t)R * Df * kRowStride +
-                (size_t)R * Dc + (size_t)R * Df + (size_t)R * Dt + (size_t)R * 8;
+                (size_t)R * Dc + (size_t)R * Df + (size_t)R * Dt * 4 + (size_t)R * 8;
     return fl * sizeof(float) + (size_t)R * Dt + 16;
 }
 }  // namespace

@@ -79,6 +79,8 @@ class Engine:
         self._tables = {}
         mask = torch.ones(1, 1, 256, 256) if uv_face_mask is None else uv_face_mask
         self.eye_mask = mask.reshape(mask.shape[-2], mask.shape[-1]).to(self.device, torch.float32).contiguous()
+        self._mm_init = torch.tensor([float('inf'), 0.0], device=self.device)
+        self._graphs = {}
 
     # ------------------------------------------------------------------------------------------ packing (one-time)
     def _add_mod(self, sd, name, cin, cout, k, up, widx, is_rgb=False, clamp=None, noise=True):
@@ -516,7 +518,7 @@ class Engine:
         return planes
 
     def synthesis(self, ws, c, v, noise_mode='const', neural_rendering_resolution=None, sampler_noise=None, seed=0,
-                  return_intermediates=False):
+                  return_intermediates=False, seed_ptr=None):
         cfg, dev = self.cfg, self.device
         N = ws.shape[0]
         R = neural_rendering_resolution or cfg.neural_rendering_resolution
@@ -531,12 +533,12 @@ class Engine:
         feat = self._f32(N, R, R, cfg.plane_ch)                                 # [N, M, 32] == NHWC feature image
         depth = self._f32(N, 1, R, R)
         wsum = self._f32(N, M)
-        mm = torch.tensor([float('inf'), 0.0], device=dev)
+        mm = self._mm_init.clone()                                          # running (min, max) of all sample depths
         u_c, u_f = sampler_noise if sampler_noise is not None else (None, None)
         if u_c is not None:
             u_c, u_f = u_c.to(dev, torch.float32).contiguous(), u_f.to(dev, torch.float32).contiguous()
         ev = self._prof_begin()
-        K.render_rays(planes, cam, intr, R, self.rk, self.dec, feat, depth, wsum, mm, u_coarse=u_c, u_fine=u_f, seed=seed)
+        K.render_rays(planes, cam, intr, R, self.rk, self.dec, feat, depth, wsum, mm, u_coarse=u_c, u_fine=u_f, seed=seed, seed_ptr=seed_ptr)
         self._prof_end(ev, 'render_rays')
         K.depth_clamp(depth, mm)
         image = self._f32(N, 3, cfg.img_resolution, cfg.img_resolution)
@@ -547,3 +549,32 @@ class Engine:
             inter.update(planes=planes, feature_image=feat, weights_sum=wsum)
             result['intermediates'] = inter
         return result
+
+    # ------------------------------------------------------------------------------------------ CUDA graph replay
+    def synthesis_graphed(self, ws, c, v, noise_mode='const', neural_rendering_resolution=None, seed=0):
+        """Same as synthesis() (in-kernel sampler RNG) but the ~250 launches of one forward are captured once per
+        (batch, resolution, noise_mode) into a CUDA graph and replayed: removes the host-side launch latency that otherwise
+        leaves the GPU idle between kernels.  Inputs are copied into static buffers; the returned tensors are the graph's
+        static outputs and are overwritten by the next call with the same key."""
+        R = neural_rendering_resolution or self.cfg.neural_rendering_resolution
+        key = (ws.shape[0], R, noise_mode, tuple(v.shape))
+        g = self._graphs.get(key)
+        if g is None:
+            st = dict(ws=torch.empty_like(ws, dtype=torch.float32), c=torch.empty_like(c, dtype=torch.float32),
+                      v=torch.empty_like(v, dtype=torch.float32), seed=torch.zeros(1, dtype=torch.int64, device=self.device))
+            st['ws'].copy_(ws); st['c'].copy_(c); st['v'].copy_(v)
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):                                   # warm-up outside capture (lazy attribute setup, allocator)
+                self.synthesis(st['ws'], st['c'], st['v'], noise_mode, R, seed=0, seed_ptr=st['seed'])
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self.synthesis(st['ws'], st['c'], st['v'], noise_mode, R, seed=0, seed_ptr=st['seed'])
+            g = self._graphs[key] = (graph, st, out, self.launches, self.conv_flops)
+        graph, st, out, launches, flops = g
+        st['ws'].copy_(ws, non_blocking=True); st['c'].copy_(c, non_blocking=True); st['v'].copy_(v, non_blocking=True)
+        st['seed'].fill_(int(seed))
+        graph.replay()
+        self.launches, self.conv_flops = launches, flops
+        return out

@@ -168,7 +168,8 @@ def blend_planes(front, tex_planes, alpha, static, planes):
           'n3d_blend_planes')
 
 
-def render_rays(planes, cam2world, intrinsics, res, opts, dec, rgb, depth, wsum, depth_minmax, u_coarse=None, u_fine=None, seed=0):
+def render_rays(planes, cam2world, intrinsics, res, opts, dec, rgb, depth, wsum, depth_minmax, u_coarse=None, u_fine=None, seed=0,
+                seed_ptr=None):
     """planes [N,3,PH,PW,32] channels-last; dec = (w0 [64,32], b0 [64], w1 [33,64], b1 [33]) with gains folded in."""
     p = _lib.Render()
     N, _, PH, PW, _ = planes.shape
@@ -176,7 +177,7 @@ def render_rays(planes, cam2world, intrinsics, res, opts, dec, rgb, depth, wsum,
     p.cam2world, p.intrinsics, p.res = ptr(cam2world), ptr(intrinsics), res
     p.depth_coarse, p.depth_fine = opts['depth_resolution'], opts['depth_resolution_importance']
     p.ray_start, p.ray_end, p.box_warp = float(opts['ray_start']), float(opts['ray_end']), float(opts['box_warp'])
-    p.u_coarse, p.u_fine, p.seed = ptr(u_coarse), ptr(u_fine), seed
+    p.u_coarse, p.u_fine, p.seed, p.seed_ptr = ptr(u_coarse), ptr(u_fine), seed, ptr(seed_ptr)
     p.w0, p.b0, p.w1, p.b1 = (ptr(t) for t in dec)
     p.rgb, p.depth, p.wsum, p.depth_minmax = ptr(rgb), ptr(depth), ptr(wsum), ptr(depth_minmax)
     p.white_back = int(bool(opts.get('white_back', False)))

@@ -71,6 +71,7 @@ class TriPlaneGenerator(torch.nn.Module):
                 _attach(self, name, torch.zeros(shape), kind in _PARAM_KINDS)
         self._engine = None
         self._engine_key = None
+        self.use_cuda_graph = False      # opt-in: replay one captured CUDA graph per (batch, resolution) instead of ~250 launches
 
     @staticmethod
     def _load_mesh(topology_path):
@@ -155,6 +156,8 @@ class TriPlaneGenerator(torch.nn.Module):
             seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) if sampler_noise is None else 0
         eng = self._get_engine()
         eng.rk = self.rendering_kwargs
+        if self.use_cuda_graph and sampler_noise is None and not synthesis_kwargs.get('return_intermediates', False):
+            return eng.synthesis_graphed(ws, c, v, noise_mode=noise_mode, neural_rendering_resolution=neural_rendering_resolution, seed=seed)
         return eng.synthesis(ws, c, v, noise_mode=noise_mode, neural_rendering_resolution=neural_rendering_resolution,
                              sampler_noise=sampler_noise, seed=seed, return_intermediates=synthesis_kwargs.get('return_intermediates', False))
 
