@@ -251,20 +251,42 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                     }
                     v[j] = a;
                 }
-                // ---- fp32 output
+                // ---- fp32 output (loads of the accumulate path are issued together, before any store, so they overlap)
                 if (P.out_f32) {
                     if (P.f32_nchw) {
-                        for (int j = 0; j < nco; ++j) {
-                            float* dst = P.out_f32 + (((int64_t)n * P.f32_cstride + P.f32_coff + co0 + j) * P.OH + oy) * P.OW + ox;
-                            *dst = P.f32_accumulate ? (*dst + v[j]) : v[j];
+                        float* dst = P.out_f32 + (((int64_t)n * P.f32_cstride + P.f32_coff + co0) * P.OH + oy) * P.OW + ox;
+                        const int64_t cs = (int64_t)P.OH * P.OW;
+                        if (P.f32_accumulate) {
+                            float old[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) old[j] = j < nco ? dst[j * cs] : 0.f;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[j] += old[j];
                         }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) if (j < nco) dst[j * cs] = v[j];
                     } else {
                         float* dst = P.out_f32 + opix * P.f32_cstride + P.f32_coff + co0;
-                        if (nco == 16 && !P.f32_accumulate && (((P.f32_cstride | (P.f32_coff + co0)) & 3) == 0)) {
+                        if (nco == 16 && (((P.f32_cstride | (P.f32_coff + co0)) & 3) == 0)) {
+                            if (P.f32_accumulate) {
+                                float4 old[4];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) old[j] = *reinterpret_cast<const float4*>(dst + 4 * j);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) { v[4 * j] += old[j].x; v[4 * j + 1] += old[j].y; v[4 * j + 2] += old[j].z; v[4 * j + 3] += old[j].w; }
+                            }
 #pragma unroll
                             for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                         } else {
-                            for (int j = 0; j < nco; ++j) dst[j] = P.f32_accumulate ? (dst[j] + v[j]) : v[j];
+                            if (P.f32_accumulate) {
+                                float old[16];
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) old[j] = j < nco ? dst[j] : 0.f;
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) v[j] += old[j];
+                            }
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) if (j < nco) dst[j] = v[j];
                         }
                     }
                 }
@@ -291,7 +313,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                                                                            pack_bf16x2(l[j + 4], l[j + 5]), pack_bf16x2(l[j + 6], l[j + 7]));
                         }
                     } else {
-                        for (int j = 0; j < nco; ++j) { dh[j] = h[j]; dl[j] = l[j]; }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) if (j < nco) { dh[j] = h[j]; dl[j] = l[j]; }
                     }
                 }
             }

@@ -74,6 +74,7 @@ class Engine:
         self.launches = 0
         self.conv_flops = 0.0
         self.prof = None
+        self._cur_layer = ''
         sd = {k: v.to(self.device, non_blocking=True) if isinstance(v, torch.Tensor) else v for k, v in state_dict.items()}
         self._pack(sd)
         self._tables = {}
@@ -210,12 +211,12 @@ class Engine:
         e0.record()
         return e0
 
-    def _prof_end(self, e0, kind, flops=0):
+    def _prof_end(self, e0, kind, flops=0, info=None):
         if e0 is None:
             return
         e1 = torch.cuda.Event(enable_timing=True)
         e1.record()
-        self.prof.append((kind, e0, e1, flops))
+        self.prof.append((kind, e0, e1, flops, info))
 
     def _gemm(self, a_hi, a_lo, w_hi, w_lo, taps, N, MH, MW, **kw):
         """n3d_conv_gemm + bookkeeping: algorithmic FLOPs = 2 * Cin * Cout * taps * M-space positions (one product)."""
@@ -223,13 +224,13 @@ class Engine:
         self.conv_flops += flops
         ev = self._prof_begin()
         K.conv_gemm(a_hi, a_lo, w_hi, w_lo, taps, N, MH, MW, **kw)
-        self._prof_end(ev, 'conv_gemm', flops)
+        self._prof_end(ev, 'conv_gemm', flops, (self._cur_layer, a_hi.shape[-1], w_hi.shape[1], MH, MW, len(taps)))
 
     def profile_summary(self):
         """After a synthesis() with self.prof = []: {kind: (launches, total_ms, total_flops)} (synchronises)."""
         torch.cuda.synchronize(self.device)
         out = {}
-        for kind, e0, e1, fl in self.prof or []:
+        for kind, e0, e1, fl, _ in self.prof or []:
             n, ms, f = out.get(kind, (0, 0.0, 0.0))
             out[kind] = (n + 1, ms + e0.elapsed_time(e1), f + fl)
         return out
@@ -261,6 +262,7 @@ class Engine:
     def _modconv(self, name, a, res_in, outs, noise_mode, f32=None):
         """SynthesisLayer (networks_stylegan2.py:311-330); `a` already carries this layer's modulation."""
         L, N = self.mod[name], self._N
+        self._cur_layer = name
         noise, nstride = self._noise(L, noise_mode)
         clamp = L.clamp if L.clamp is not None else -1.0
         if L.up == 1:
@@ -282,6 +284,7 @@ class Engine:
     def _torgb(self, name, a, res, img, accumulate, nchw=False):
         """ToRGBLayer (networks_stylegan2.py:353-357): 1x1 modulated conv without demodulation, linear bias (+ clamp)."""
         L = self.mod[name]
+        self._cur_layer = name
         self._gemm(a.hi, a.lo, L.w_hi, L.w_lo, K.taps_conv1x1(), self._N, res, res, nprod=self.nprod, bias=L.bias,
                     clamp=L.clamp if L.clamp is not None else -1.0, out_f32=img, f32_cstride=L.cout, f32_nchw=nchw, f32_accumulate=accumulate)
         self.launches += 1
@@ -289,6 +292,7 @@ class Engine:
     def _plainconv(self, name, a, res, act, outs=(), f32=None, accumulate=False, stride2=False):
         """styleunet Conv2dLayer (networks_stylegan2_styleunet.py:198-207): weight_gain folded into the packed weights."""
         L, N = self.plain[name], self._N
+        self._cur_layer = name
         gain, slope = (SQRT2, 0.2) if act == 'lrelu' else (1.0, 1.0)
         if stride2:
             self._gemm(a.hi, a.lo, L.w_hi, L.w_lo, K.taps_stride2(), N, res // 2, res // 2, a_img_mul=N, nprod=self.nprod, bias=L.bias, gain=gain,
