@@ -20,9 +20,10 @@
 namespace {
 
 constexpr int kBlockM = 128;
-constexpr int kBlockK = 64;                    // bf16 elements = 128 bytes = one swizzle row
-constexpr int kABytes = kBlockM * kBlockK * 2; // 16 KiB per A tile
-constexpr int kThreads = 256;
+// K per pipeline stage: 64 bf16 (128-byte rows, SWIZZLE_128B) or, for Cin % 64 == 32 (the 32-channel feature images),
+// 32 bf16 (64-byte rows, SWIZZLE_64B) so that no TMA box hangs over the channel extent.
+constexpr int kThreads = 384;                 // warps 0-3: producer / MMA / TMEM alloc / spare; 4-7 and 8-11: two epilogue groups
+constexpr int kMaxBlockN = 256;
 constexpr uint32_t kSpinLimit = 1u << 24;
 
 struct KParams {
@@ -30,7 +31,7 @@ struct KParams {
     int N, MH, MW, Cout;
     int TW, TH, TN;                  // TW*TH*TN == 128, all powers of two
     int tiles_x, tiles_y, tiles_i, tiles_n;
-    int block_n, acc_stride, tmem_cols, stages, stage_bytes, b_bytes;
+    int block_n, acc_stride, tmem_cols, stages, stage_bytes, b_bytes, a_bytes, block_k;
     int cin_chunks, ntaps, nprod, a_img_stride;
     N3DConvTap taps[9];
     int mode;
@@ -88,9 +89,13 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46) = 1024 B between 8-row groups, version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
-           ((uint64_t)2 << 61);
+// `hi32` carries SBO / version / layout: SWIZZLE_128B -> SBO 1024, layout 2; SWIZZLE_64B -> SBO 512, layout 4.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint64_t hi_bits) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | hi_bits;
+}
+__device__ __forceinline__ uint64_t umma_desc_hi(int block_k) {
+    return block_k == 64 ? (((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61))
+                         : (((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61));
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -125,6 +130,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     auto tfull_bar = [&](int a) { return bar_base + 8u * (uint32_t)(2 * P.stages + a); };
     auto tempty_bar = [&](int a) { return bar_base + 8u * (uint32_t)(2 * P.stages + 2 + a); };
     const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(2 * P.stages + 4);
+    const uint32_t stage_area_off = ((tmem_slot + 16u + 15u) & ~15u) - smem_u32(smem_raw);   // byte offset of the epilogue staging area
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -155,7 +161,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         // ===================================================== TMA producer
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;
-            const uint32_t tx_bytes = (uint32_t)(P.nprod == 3 ? 2 : 1) * (uint32_t)(kABytes + P.b_bytes);
+            const uint32_t tx_bytes = (uint32_t)(P.nprod == 3 ? 2 : 1) * (uint32_t)(P.a_bytes + P.b_bytes);
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int tn = tile % P.tiles_n, tm = tile / P.tiles_n;
                 const int x0 = (tm % P.tiles_x) * P.TW, y0 = ((tm / P.tiles_x) % P.tiles_y) * P.TH;
@@ -168,11 +174,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                         const uint32_t fb = full_bar(s);
                         mbar_expect_tx(fb, tx_bytes);
                         const int img = n0 + (int)tap.img_off * P.a_img_stride;
-                        tma_load_4d(sa, &P.tmA_hi, fb, kc * kBlockK, x0 + tap.dx, y0 + tap.dy, img);
-                        tma_load_3d(sa + 2 * kABytes, &P.tmB_hi, fb, kc * kBlockK, tn * P.block_n, tap.wtap);
+                        tma_load_4d(sa, &P.tmA_hi, fb, kc * P.block_k, x0 + tap.dx, y0 + tap.dy, img);
+                        tma_load_3d(sa + 2 * P.a_bytes, &P.tmB_hi, fb, kc * P.block_k, tn * P.block_n, tap.wtap);
                         if (P.nprod == 3) {
-                            tma_load_4d(sa + kABytes, &P.tmA_lo, fb, kc * kBlockK, x0 + tap.dx, y0 + tap.dy, img);
-                            tma_load_3d(sa + 2 * kABytes + P.b_bytes, &P.tmB_lo, fb, kc * kBlockK, tn * P.block_n, tap.wtap);
+                            tma_load_4d(sa + P.a_bytes, &P.tmA_lo, fb, kc * P.block_k, x0 + tap.dx, y0 + tap.dy, img);
+                            tma_load_3d(sa + 2 * P.a_bytes + P.b_bytes, &P.tmB_lo, fb, kc * P.block_k, tn * P.block_n, tap.wtap);
                         }
                         if (++s == P.stages) { s = 0; ph ^= 1u; }
                     }
@@ -185,6 +191,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
             // both K-major, N>>3 at [17,23), M>>4 at [24,29)
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.block_n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+            const uint64_t dhi = umma_desc_hi(P.block_k);
+            const int k16 = P.block_k / 16;
             int s = 0; uint32_t ph = 0; int acc = 0; uint32_t acc_ph = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 mbar_wait(tempty_bar(acc), acc_ph ^ 1u, P.err_flag, 2);
@@ -194,14 +202,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                     mbar_wait(full_bar(s), ph, P.err_flag, 3);
                     tc_fence_after();
                     const uint32_t sa = smem_base + (uint32_t)s * (uint32_t)P.stage_bytes;
-                    const uint32_t a_hi = sa, a_lo = sa + kABytes, b_hi = sa + 2 * kABytes, b_lo = b_hi + (uint32_t)P.b_bytes;
-#pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k) {
-                        const uint32_t koff = (uint32_t)k * 32u;     // 16 bf16 = 32 bytes inside the 128-B swizzle row
-                        umma_bf16(d_tmem, umma_desc(a_hi + koff), umma_desc(b_hi + koff), idesc, (ks | k) != 0);
+                    const uint32_t a_hi = sa, a_lo = sa + (uint32_t)P.a_bytes, b_hi = sa + 2u * (uint32_t)P.a_bytes, b_lo = b_hi + (uint32_t)P.b_bytes;
+                    for (int k = 0; k < k16; ++k) {
+                        const uint32_t koff = (uint32_t)k * 32u;     // 16 bf16 = 32 bytes inside the swizzle row
+                        umma_bf16(d_tmem, umma_desc(a_hi + koff, dhi), umma_desc(b_hi + koff, dhi), idesc, (ks | k) != 0);
                         if (P.nprod == 3) {
-                            umma_bf16(d_tmem, umma_desc(a_hi + koff), umma_desc(b_lo + koff), idesc, 1u);
-                            umma_bf16(d_tmem, umma_desc(a_lo + koff), umma_desc(b_hi + koff), idesc, 1u);
+                            umma_bf16(d_tmem, umma_desc(a_hi + koff, dhi), umma_desc(b_lo + koff, dhi), idesc, 1u);
+                            umma_bf16(d_tmem, umma_desc(a_lo + koff, dhi), umma_desc(b_hi + koff, dhi), idesc, 1u);
                         }
                     }
                     umma_commit(empty_bar(s));                 // frees the smem stage once these MMAs retire
@@ -212,24 +219,44 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             }
         }
     } else if (warp >= 4) {
-        // ===================================================== epilogue (4 warps = 128 TMEM lanes)
+        // ===================================================== epilogue: 2 groups x 4 warps; group g drains TMEM accumulator g
+        const int g = (warp - 4) >> 2;                         // epilogue group == accumulator buffer it serves
         const int q = warp & 3;                                // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;                         // tile row = TMEM lane
+        const int gtid = (warp - 4 - 4 * g) * 32 + lane;       // thread index inside the group (0..127)
         const int tw = row % P.TW, th = (row / P.TW) % P.TH, tnn = row / (P.TW * P.TH);
-        int acc = 0; uint32_t acc_ph = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        // per-group staging of the per-channel epilogue vectors of the current tile: [dcoef | bias | style0 | style1][block_n]
+        float* stg = reinterpret_cast<float*>(smem_raw + (stage_area_off + (uint32_t)g * 4u * (uint32_t)kMaxBlockN * 4u));
+        const bool staged = (P.TN == 1) && (P.mode == 0);
+        uint32_t acc_ph = 0;
+        for (int tile = blockIdx.x + g * gridDim.x; tile < total_tiles; tile += 2 * gridDim.x) {
             const int tn = tile % P.tiles_n, tm = tile / P.tiles_n;
             const int x = (tm % P.tiles_x) * P.TW + tw, y = ((tm / P.tiles_x) % P.tiles_y) * P.TH + th;
-            const int n = (tm / (P.tiles_x * P.tiles_y)) * P.TN + tnn;
+            const int n0 = (tm / (P.tiles_x * P.tiles_y)) * P.TN;
+            const int n = n0 + tnn;
             const int oy = y * P.oy_mul + P.oy_off, ox = x * P.ox_mul + P.ox_off;
             const bool valid = (n < P.N) && (y < P.MH) && (x < P.MW) && (oy < P.OH) && (ox < P.OW);
             const int64_t opix = ((int64_t)n * P.OH + oy) * P.OW + ox;
             float nz = 0.f;
             if (valid && P.noise) nz = __ldg(P.noise + (int64_t)n * P.noise_nstride + (int64_t)oy * P.OW + ox);
+            if (staged) {
+                // all 4 warps of the group are done with the previous tile's vectors before they are overwritten
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+                for (int i = gtid; i < 4 * P.block_n; i += 128) {
+                    const int arr = i / P.block_n, c = i - arr * P.block_n, co = tn * P.block_n + c;
+                    float val = arr == 1 ? 0.f : 1.f;
+                    if (co < P.Cout && n0 < P.N) {
+                        const float* src = arr == 0 ? P.dcoef : arr == 1 ? P.bias : (arr == 2 ? P.out[0].style : P.out[1].style);
+                        if (src) val = __ldg(src + (arr == 1 ? (int64_t)co : (int64_t)n0 * P.Cout + co));
+                    }
+                    stg[arr * kMaxBlockN + c] = val;
+                }
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+            }
 
-            mbar_wait(tfull_bar(acc), acc_ph, P.err_flag, 4);
+            mbar_wait(tfull_bar(g), acc_ph, P.err_flag, 4);
             tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * P.acc_stride);
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * P.acc_stride);
             for (int c16 = 0; c16 < P.block_n; c16 += 16) {
                 uint32_t r[16];
                 __syncwarp();                                  // tcgen05.ld is warp-collective (.sync.aligned)
@@ -237,19 +264,43 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 const int co0 = tn * P.block_n + c16;
                 if (!valid || co0 >= P.Cout) continue;
                 const int nco = min(16, P.Cout - co0);
-                float v[16];
+                float v[16], s0[16], s1[16];
+                if (staged) {
+                    const float4* d4 = reinterpret_cast<const float4*>(stg + c16);
+                    const float4* b4 = reinterpret_cast<const float4*>(stg + kMaxBlockN + c16);
+                    const float4* p4 = reinterpret_cast<const float4*>(stg + 2 * kMaxBlockN + c16);
+                    const float4* q4 = reinterpret_cast<const float4*>(stg + 3 * kMaxBlockN + c16);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    float a = __uint_as_float(r[j]);
-                    if (P.mode == 0 && j < nco) {
-                        const int co = co0 + j;
-                        if (P.dcoef) a *= __ldg(P.dcoef + (int64_t)n * P.Cout + co);
-                        a += nz;
-                        if (P.bias) a += __ldg(P.bias + co);
-                        a = (a > 0.f ? a : a * P.slope) * P.gain;
-                        if (P.clamp >= 0.f) a = fminf(fmaxf(a, -P.clamp), P.clamp);
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        const float4 d = d4[j4], bb = b4[j4], ps = p4[j4], qs = q4[j4];
+                        const float dd[4] = {d.x, d.y, d.z, d.w}, bv[4] = {bb.x, bb.y, bb.z, bb.w};
+                        const float pv[4] = {ps.x, ps.y, ps.z, ps.w}, qv[4] = {qs.x, qs.y, qs.z, qs.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int j = j4 * 4 + e;
+                            float a = __uint_as_float(r[j]) * dd[e] + nz + bv[e];
+                            a = (a > 0.f ? a : a * P.slope) * P.gain;
+                            if (P.clamp >= 0.f) a = fminf(fmaxf(a, -P.clamp), P.clamp);
+                            v[j] = a; s0[j] = pv[e]; s1[j] = qv[e];
+                        }
                     }
-                    v[j] = a;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float a = __uint_as_float(r[j]);
+                        s0[j] = 1.f; s1[j] = 1.f;
+                        if (P.mode == 0 && j < nco) {
+                            const int co = co0 + j;
+                            if (P.dcoef) a *= __ldg(P.dcoef + (int64_t)n * P.Cout + co);
+                            a += nz;
+                            if (P.bias) a += __ldg(P.bias + co);
+                            a = (a > 0.f ? a : a * P.slope) * P.gain;
+                            if (P.clamp >= 0.f) a = fminf(fmaxf(a, -P.clamp), P.clamp);
+                            if (P.out[0].style) s0[j] = __ldg(P.out[0].style + (int64_t)n * P.Cout + co);
+                            if (P.out[1].style) s1[j] = __ldg(P.out[1].style + (int64_t)n * P.Cout + co);
+                        }
+                        v[j] = a;
+                    }
                 }
                 // ---- fp32 output (loads of the accumulate path are issued together, before any store, so they overlap)
                 if (P.out_f32) {
@@ -297,11 +348,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                     if (!o.hi) continue;
                     __nv_bfloat16 h[16], l[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float s = v[j];
-                        if (o.style && j < nco) s *= __ldg(o.style + (int64_t)n * P.Cout + co0 + j);
-                        split_bf16(s, h[j], l[j]);
-                    }
+                    for (int j = 0; j < 16; ++j) split_bf16(v[j] * (k == 0 ? s0[j] : s1[j]), h[j], l[j]);
                     __nv_bfloat16* dh = (__nv_bfloat16*)o.hi + opix * o.cstride + o.coff + co0;
                     __nv_bfloat16* dl = (__nv_bfloat16*)o.lo + opix * o.cstride + o.coff + co0;
                     if (nco == 16 && (((o.cstride | (o.coff + co0)) & 7) == 0)) {
@@ -320,8 +367,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));
-            if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+            if (lane == 0) mbar_arrive(tempty_bar(g));
+            acc_ph ^= 1u;
         }
     }
 
@@ -348,7 +395,7 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint32_t* box) {
+int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint32_t* box, int block_k) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) { n3d_set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return N3D_ERR_CUDA; }
     cuuint64_t gdim[5], gstr[5];
@@ -360,7 +407,7 @@ int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
         if (i < rank - 1) gstr[i] = stride;      // byte stride of dim i+1
     }
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { n3d_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return N3D_ERR_CUDA; }
     return N3D_OK;
@@ -409,10 +456,12 @@ extern "C" int n3d_conv_gemm(const N3DConvGemm* p, void* stream) {
     K.tiles_n = n3d_div_up(p->Cout, bn);
     K.acc_stride = max(32, pow2_ceil(bn));
     K.tmem_cols = 2 * K.acc_stride;
-    K.b_bytes = bn * kBlockK * 2;
-    K.stage_bytes = 2 * kABytes + 2 * K.b_bytes;
-    K.stages = min(6, (200 * 1024) / K.stage_bytes);
-    K.cin_chunks = n3d_div_up(p->Cin, kBlockK);
+    K.block_k = (p->Cin % 64 == 0 || p->Cin % 32 != 0) ? 64 : 32;
+    K.a_bytes = kBlockM * K.block_k * 2;
+    K.b_bytes = bn * K.block_k * 2;
+    K.stage_bytes = 2 * K.a_bytes + 2 * K.b_bytes;
+    K.stages = min(6, (200 * 1024) / K.stage_bytes);      // + 8 KiB epilogue staging + barriers + 1 KiB alignment slack <= 227 KiB
+    K.cin_chunks = n3d_div_up(p->Cin, K.block_k);
     K.ntaps = p->ntaps; K.nprod = p->nprod; K.a_img_stride = p->a_img_mul;
     for (int i = 0; i < p->ntaps; ++i) {
         K.taps[i] = p->taps[i];
@@ -431,18 +480,18 @@ extern "C" int n3d_conv_gemm(const N3DConvGemm* p, void* stream) {
     K.err_flag = g_err_flag;
 
     const uint64_t adims[4] = {(uint64_t)p->Cin, (uint64_t)p->AW, (uint64_t)p->AH, (uint64_t)p->NI};
-    const uint32_t abox[4] = {(uint32_t)kBlockK, (uint32_t)K.TW, (uint32_t)K.TH, (uint32_t)K.TN};
+    const uint32_t abox[4] = {(uint32_t)K.block_k, (uint32_t)K.TW, (uint32_t)K.TH, (uint32_t)K.TN};
     const uint64_t wdims[3] = {(uint64_t)p->Cin, (uint64_t)p->Cout, (uint64_t)p->T};
-    const uint32_t wbox[3] = {(uint32_t)kBlockK, (uint32_t)bn, 1u};
+    const uint32_t wbox[3] = {(uint32_t)K.block_k, (uint32_t)bn, 1u};
     int rc;
-    if ((rc = make_tmap(&K.tmA_hi, p->a_hi, 4, adims, abox)) != N3D_OK) return rc;
-    if ((rc = make_tmap(&K.tmB_hi, p->w_hi, 3, wdims, wbox)) != N3D_OK) return rc;
+    if ((rc = make_tmap(&K.tmA_hi, p->a_hi, 4, adims, abox, K.block_k)) != N3D_OK) return rc;
+    if ((rc = make_tmap(&K.tmB_hi, p->w_hi, 3, wdims, wbox, K.block_k)) != N3D_OK) return rc;
     if (p->nprod == 3) {
-        if ((rc = make_tmap(&K.tmA_lo, p->a_lo, 4, adims, abox)) != N3D_OK) return rc;
-        if ((rc = make_tmap(&K.tmB_lo, p->w_lo, 3, wdims, wbox)) != N3D_OK) return rc;
+        if ((rc = make_tmap(&K.tmA_lo, p->a_lo, 4, adims, abox, K.block_k)) != N3D_OK) return rc;
+        if ((rc = make_tmap(&K.tmB_lo, p->w_lo, 3, wdims, wbox, K.block_k)) != N3D_OK) return rc;
     }
 
-    const int smem = K.stages * K.stage_bytes + 8 * (2 * K.stages + 4) + 16 + 1024;
+    const int smem = K.stages * K.stage_bytes + 8 * (2 * K.stages + 4) + 32 + 2 * 4 * kMaxBlockN * 4 + 1024;
     static int smem_configured = 0;
     if (smem > smem_configured) {
         if (cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
