@@ -47,34 +47,40 @@ __device__ __forceinline__ float linspace_at(float start, float end, int steps, 
     return i < steps / 2 ? start + step * (float)i : end - step * (float)(steps - 1 - i);
 }
 
-// bilinear fetch of one plane at grid coords (gx, gy) for channel `lane` (zeros padding, align_corners=False)
-__device__ __forceinline__ float plane_fetch(const float* __restrict__ plane, int PH, int PW, float gx, float gy, int lane) {
+// Bilinear tap setup for one plane at grid coords (gx, gy) (grid_sample: zeros padding, align_corners=False).  Out-of-range
+// taps get weight 0 and a clamped (always valid) address so that all loads can be issued unconditionally and together.
+struct Taps { const float* p[4]; float w[4]; };
+__device__ __forceinline__ Taps plane_taps(const float* __restrict__ plane, int PH, int PW, float gx, float gy, int lane) {
     const float ix = ((gx + 1.f) * (float)PW - 1.f) * 0.5f, iy = ((gy + 1.f) * (float)PH - 1.f) * 0.5f;
     const float flx = floorf(ix), fly = floorf(iy);
     const int x0 = (int)flx, y0 = (int)fly;
     const float fx = ix - flx, fy = iy - fly;
-    float acc = 0.f;
     const bool xin0 = x0 >= 0 && x0 < PW, xin1 = x0 + 1 >= 0 && x0 + 1 < PW;
-    if (y0 >= 0 && y0 < PH) {
-        const float* r = plane + ((int64_t)y0 * PW) * kFeat + lane;
-        if (xin0) acc += (1.f - fx) * (1.f - fy) * __ldg(r + (int64_t)x0 * kFeat);
-        if (xin1) acc += fx * (1.f - fy) * __ldg(r + (int64_t)(x0 + 1) * kFeat);
-    }
-    if (y0 + 1 >= 0 && y0 + 1 < PH) {
-        const float* r = plane + ((int64_t)(y0 + 1) * PW) * kFeat + lane;
-        if (xin0) acc += (1.f - fx) * fy * __ldg(r + (int64_t)x0 * kFeat);
-        if (xin1) acc += fx * fy * __ldg(r + (int64_t)(x0 + 1) * kFeat);
-    }
-    return acc;
+    const bool yin0 = y0 >= 0 && y0 < PH, yin1 = y0 + 1 >= 0 && y0 + 1 < PH;
+    const int xc0 = min(max(x0, 0), PW - 1), xc1 = min(max(x0 + 1, 0), PW - 1);
+    const int yc0 = min(max(y0, 0), PH - 1), yc1 = min(max(y0 + 1, 0), PH - 1);
+    Taps t;
+    t.p[0] = plane + ((int64_t)yc0 * PW + xc0) * kFeat + lane; t.w[0] = (xin0 && yin0) ? (1.f - fx) * (1.f - fy) : 0.f;
+    t.p[1] = plane + ((int64_t)yc0 * PW + xc1) * kFeat + lane; t.w[1] = (xin1 && yin0) ? fx * (1.f - fy) : 0.f;
+    t.p[2] = plane + ((int64_t)yc1 * PW + xc0) * kFeat + lane; t.w[2] = (xin0 && yin1) ? (1.f - fx) * fy : 0.f;
+    t.p[3] = plane + ((int64_t)yc1 * PW + xc1) * kFeat + lane; t.w[3] = (xin1 && yin1) ? fx * fy : 0.f;
+    return t;
 }
 
-// mean over the three planes of the bilinear features at world point (px,py,pz); plane 0 <- (x,y), 1 <- (x,z), 2 <- (z,y)
+// mean over the three planes of the bilinear features at world point (px,py,pz); plane 0 <- (x,y), 1 <- (x,z), 2 <- (z,y).
+// The 12 loads (each one coalesced 128-byte line across the warp) are issued back to back before any is consumed.
 __device__ __forceinline__ float triplane_feature(const float* __restrict__ planes_n, int PH, int PW, float px, float py, float pz, float scale, int lane) {
     const float x = scale * px, y = scale * py, z = scale * pz;
     const int64_t ps = (int64_t)PH * PW * kFeat;
-    const float f0 = plane_fetch(planes_n, PH, PW, x, y, lane);
-    const float f1 = plane_fetch(planes_n + ps, PH, PW, x, z, lane);
-    const float f2 = plane_fetch(planes_n + 2 * ps, PH, PW, z, y, lane);
+    const Taps t0 = plane_taps(planes_n, PH, PW, x, y, lane);
+    const Taps t1 = plane_taps(planes_n + ps, PH, PW, x, z, lane);
+    const Taps t2 = plane_taps(planes_n + 2 * ps, PH, PW, z, y, lane);
+    float v0[4], v1[4], v2[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v0[i] = __ldg(t0.p[i]); v1[i] = __ldg(t1.p[i]); v2[i] = __ldg(t2.p[i]); }
+    float f0 = 0.f, f1 = 0.f, f2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { f0 += t0.w[i] * v0[i]; f1 += t1.w[i] * v1[i]; f2 += t2.w[i] * v2[i]; }
     return ((f0 + f1) + f2) / 3.f;
 }
 
@@ -226,16 +232,14 @@ __global__ void __launch_bounds__(kMaxThreads) render_kernel(const RenderK K) {
     const int64_t plane_img = (int64_t)3 * P.PH * P.PW * kFeat;
 
     // ---- coarse pass: gather (warp per sample) then decode (thread per sample)
+#pragma unroll 2
     for (int s = warp; s < R * Dc; s += nwarps) {
         const int r = s / Dc;
-        const int64_t gr = ray0 + r;
-        float feat = 0.f;
-        if (gr < total_rays) {
-            const float* ry = sRay + r * 8;
-            const float t = sTc[s];
-            feat = triplane_feature(P.planes + (gr / K.M) * plane_img, P.PH, P.PW, ry[0] + t * ry[3], ry[1] + t * ry[4], ry[2] + t * ry[5], scale, lane);
-        }
-        sC[s * kRowStride + lane] = feat;
+        const int64_t gr = min(ray0 + r, total_rays - 1);        // tail rays recompute the last valid ray (never stored)
+        const float* ry = sRay + r * 8;
+        const float t = sTc[s];
+        sC[s * kRowStride + lane] = triplane_feature(P.planes + (gr / K.M) * plane_img, P.PH, P.PW, ry[0] + t * ry[3], ry[1] + t * ry[4],
+                                                     ry[2] + t * ry[5], scale, lane);
     }
     __syncthreads();
     for (int s = tid; s < R * Dc; s += blockDim.x) decode_row(sC + s * kRowStride, sW0, sB0, sW1t, sB1);
@@ -297,16 +301,14 @@ __global__ void __launch_bounds__(kMaxThreads) render_kernel(const RenderK K) {
     __syncthreads();
 
     // ---- fine pass
+#pragma unroll 2
     for (int s = warp; s < R * Df; s += nwarps) {
         const int r = s / Df;
-        const int64_t gr = ray0 + r;
-        float feat = 0.f;
-        if (gr < total_rays) {
-            const float* ry = sRay + r * 8;
-            const float t = sTf[s];
-            feat = triplane_feature(P.planes + (gr / K.M) * plane_img, P.PH, P.PW, ry[0] + t * ry[3], ry[1] + t * ry[4], ry[2] + t * ry[5], scale, lane);
-        }
-        sF[s * kRowStride + lane] = feat;
+        const int64_t gr = min(ray0 + r, total_rays - 1);
+        const float* ry = sRay + r * 8;
+        const float t = sTf[s];
+        sF[s * kRowStride + lane] = triplane_feature(P.planes + (gr / K.M) * plane_img, P.PH, P.PW, ry[0] + t * ry[3], ry[1] + t * ry[4],
+                                                     ry[2] + t * ry[5], scale, lane);
     }
     __syncthreads();
     for (int s = tid; s < R * Df; s += blockDim.x) decode_row(sF + s * kRowStride, sW0, sB0, sW1t, sB1);
