@@ -79,15 +79,21 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
+def _cpu_threads():
+    """Threads for the CPU arm.  Measured on the GPU box's 128-core host (tools/cpu_probe.py, batch 1): 8 threads 2.30 s/img,
+    16 -> 1.98, 32 -> 2.41, 64 -> 3.75, 128 -> 101.9 (oversubscription of many small convolutions): use the fastest setting."""
+    return int(os.environ.get('N3D_CPU_THREADS', min(os.cpu_count() or 1, 16)))
+
+
 def run_reference(args):
-    """CPU arm: the oracle port of the reference's CPU path, all host threads, one image per step."""
+    """CPU arm: the oracle port of the reference's CPU path on the host cores, one image per step."""
     import torch
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     from next3d_b200 import config, weights
     from oracle import generator as og
-    cores = os.cpu_count()
+    cores = _cpu_threads()
     torch.set_num_threads(cores)
     cfg = config.full_config(512)
     sd = weights.make_state_dict(cfg, seed=0)
@@ -102,7 +108,7 @@ def run_reference(args):
             og.synthesis(sd, cfg, ws, c_cam, v, u_c, u_f)
         dt = time.perf_counter() - t0
     val = args.steps / dt
-    sample = f'{args.steps} steps x 1 image (batch 1) of the same generator/config, fp32 torch CPU ops, {cores} threads'
+    sample = f'{args.steps} steps x 1 image (batch 1) of the same generator/config, fp32 torch CPU ops, {cores} threads (of {os.cpu_count()} host cores; more threads are slower, see bench.py::_cpu_threads)'
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
@@ -116,7 +122,7 @@ def cpu_baseline_sample():
     import torch
     from next3d_b200 import config, weights
     from oracle import generator as og
-    cores = os.cpu_count()
+    cores = _cpu_threads()
     torch.set_num_threads(cores)
     cfg = config.full_config(512)
     sd = weights.make_state_dict(cfg, seed=0)
@@ -132,7 +138,7 @@ def cpu_baseline_sample():
             times.append(time.perf_counter() - t0)
     med = statistics.median(times)
     return {'value': 1.0 / med, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-            'sample': '1 warm-up + median of 3 synthesis() calls, batch 1, same weights/config, CPU oracle port (fp32 torch ops)'}
+            'sample': f'1 warm-up + median of 3 synthesis() calls, batch 1, same weights/config, CPU oracle port (fp32 torch ops), {cores} of {os.cpu_count()} host threads (fastest setting)'}
 
 
 def run_ours(args):
