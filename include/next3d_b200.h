@@ -114,8 +114,6 @@ typedef struct {
     int32_t a_img_mul;                       /* image coordinate = n + tap.img_off * a_img_mul (parity-major sub-images: = N) */
     int32_t ntaps; N3DConvTap taps[9];
     int32_t nprod;                           /* 3 = hi*hi + hi*lo + lo*hi (fp32-grade), 1 = hi*hi only */
-    int32_t ksplit;                          /* > 1: split the K loop over that many CTAs per tile (mode 1 only; out_f32 must be zeroed,
-                                                partial sums are reduced with red.global.add.f32) -- for the 4^2..32^2 layers */
     int32_t mode;
     const float* dcoef;                      /* [N, Cout] or NULL */
     const float* bias;                       /* [Cout] or NULL */
@@ -128,12 +126,6 @@ typedef struct {
 } N3DConvGemm;
 
 int n3d_conv_gemm(const N3DConvGemm* p, void* stream);
-
-/* Pointwise epilogue for raw conv outputs produced in mode 1 (split-K layers): same math as n3d_conv_gemm's mode-0 epilogue,
- * raw fp32 NHWC [N,H,W,C] -> demod/noise/bias/lrelu/clamp -> split outputs / fp32. */
-int n3d_epilogue(const float* raw, int N, int H, int W, int C, const float* dcoef, const float* bias, const float* noise,
-                 int64_t noise_nstride, float gain, float slope, float clamp, const N3DSplitOut out[2], float* out_f32,
-                 int f32_cstride, int f32_coff, void* stream);
 
 /* fp32 NHWC -> split bf16 NHWC with optional per-(n,c) modulation: out = split(x[n,y,x,c] * style[n,c]). */
 int n3d_modulate_split(const float* x, int64_t npix_per_img, int N, int C, const float* style, void* hi, void* lo,

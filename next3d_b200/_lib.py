@@ -36,7 +36,7 @@ class ConvGemm(C.Structure):
         ('w_hi', P), ('w_lo', P), ('T', I32), ('Cout', I32),
         ('N', I32), ('MH', I32), ('MW', I32), ('a_img_mul', I32),
         ('ntaps', I32), ('taps', ConvTap * 9),
-        ('nprod', I32), ('ksplit', I32), ('mode', I32),
+        ('nprod', I32), ('mode', I32),
         ('dcoef', P), ('bias', P), ('noise', P), ('noise_nstride', I64),
         ('gain', F32), ('slope', F32), ('clamp', F32),
         ('out', SplitOut * 2),
@@ -67,7 +67,6 @@ _SIGNATURES = {
     'n3d_conv_gemm': ([C.POINTER(ConvGemm), P], C.c_int),
     'n3d_modulate_split': ([P, I64, C.c_int, C.c_int, P, P, P, C.c_int, C.c_int, P], C.c_int),
     'n3d_fir_up_epilogue': ([P, C.c_int, C.c_int, C.c_int, C.c_int, P, P, P, I64, F32, F32, F32, C.POINTER(SplitOut), P, C.c_int, C.c_int, P], C.c_int),
-    'n3d_epilogue': ([P, C.c_int, C.c_int, C.c_int, C.c_int, P, P, P, I64, F32, F32, F32, C.POINTER(SplitOut), P, C.c_int, C.c_int, P], C.c_int),
     'n3d_fir_down_split': ([P, C.c_int, C.c_int, C.c_int, C.c_int, P, P, P], C.c_int),
     'n3d_upsample2d_nhwc': ([P, C.c_int, C.c_int, C.c_int, C.c_int, P, C.c_int, P], C.c_int),
     'n3d_downsample2d_nhwc': ([P, C.c_int, C.c_int, C.c_int, C.c_int, P, P], C.c_int),

@@ -33,7 +33,6 @@ struct KParams {
     int tiles_x, tiles_y, tiles_i, tiles_n;
     int block_n, acc_stride, tmem_cols, stages, stage_bytes, b_bytes, a_bytes, block_k;
     int cin_chunks, ntaps, nprod, a_img_stride;
-    int ksplit, ksteps_per_split;    // split-K: work item = (tile, split); splits accumulate with red.global.add.f32 (mode 1 only)
     N3DConvTap taps[9];
     int mode;
     const float* dcoef; const float* bias; const float* noise; int64_t noise_nstride;
@@ -155,7 +154,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
     const int tiles_m = P.tiles_x * P.tiles_y * P.tiles_i;
-    const int total_tiles = tiles_m * P.tiles_n * P.ksplit;      // work items: (tile, k-split), split index fastest
+    const int total_tiles = tiles_m * P.tiles_n;
     const int ksteps = P.ntaps * P.cin_chunks;
 
     if (warp == 0) {
@@ -163,16 +162,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;
             const uint32_t tx_bytes = (uint32_t)(P.nprod == 3 ? 2 : 1) * (uint32_t)(P.a_bytes + P.b_bytes);
-            for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
-                const int tile = item / P.ksplit, ksi = item - tile * P.ksplit;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int tn = tile % P.tiles_n, tm = tile / P.tiles_n;
                 const int x0 = (tm % P.tiles_x) * P.TW, y0 = ((tm / P.tiles_x) % P.tiles_y) * P.TH;
                 const int n0 = (tm / (P.tiles_x * P.tiles_y)) * P.TN;
-                const int k_begin = ksi * P.ksteps_per_split, k_end = min(ksteps, k_begin + P.ksteps_per_split);
-                {
-                    for (int kk = k_begin; kk < k_end; ++kk) {
-                        const int t = kk / P.cin_chunks, kc = kk - t * P.cin_chunks;
-                        const N3DConvTap tap = P.taps[t];
+                for (int t = 0; t < P.ntaps; ++t) {
+                    const N3DConvTap tap = P.taps[t];
+                    for (int kc = 0; kc < P.cin_chunks; ++kc) {
                         mbar_wait(empty_bar(s), ph ^ 1u, P.err_flag, 1);
                         const uint32_t sa = smem_base + (uint32_t)s * (uint32_t)P.stage_bytes;
                         const uint32_t fb = full_bar(s);
@@ -198,13 +194,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             const uint64_t dhi = umma_desc_hi(P.block_k);
             const int k16 = P.block_k / 16;
             int s = 0; uint32_t ph = 0; int acc = 0; uint32_t acc_ph = 0;
-            for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
-                const int ksi = item % P.ksplit;
-                const int nks = min(ksteps, (ksi + 1) * P.ksteps_per_split) - ksi * P.ksteps_per_split;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 mbar_wait(tempty_bar(acc), acc_ph ^ 1u, P.err_flag, 2);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P.acc_stride);
-                for (int ks = 0; ks < nks; ++ks) {
+                for (int ks = 0; ks < ksteps; ++ks) {
                     mbar_wait(full_bar(s), ph, P.err_flag, 3);
                     tc_fence_after();
                     const uint32_t sa = smem_base + (uint32_t)s * (uint32_t)P.stage_bytes;
@@ -235,8 +229,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         float* stg = reinterpret_cast<float*>(smem_raw + (stage_area_off + (uint32_t)g * 4u * (uint32_t)kMaxBlockN * 4u));
         const bool staged = (P.TN == 1) && (P.mode == 0);
         uint32_t acc_ph = 0;
-        for (int item = blockIdx.x + g * gridDim.x; item < total_tiles; item += 2 * gridDim.x) {
-            const int tile = item / P.ksplit;
+        for (int tile = blockIdx.x + g * gridDim.x; tile < total_tiles; tile += 2 * gridDim.x) {
             const int tn = tile % P.tiles_n, tm = tile / P.tiles_n;
             const int x = (tm % P.tiles_x) * P.TW + tw, y = ((tm / P.tiles_x) % P.tiles_y) * P.TH + th;
             const int n0 = (tm / (P.tiles_x * P.tiles_y)) * P.TN;
@@ -325,10 +318,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                         for (int j = 0; j < 16; ++j) if (j < nco) dst[j * cs] = v[j];
                     } else {
                         float* dst = P.out_f32 + opix * P.f32_cstride + P.f32_coff + co0;
-                        if (P.ksplit > 1) {                    // partial sums of this k-split: reduce in L2
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) if (j < nco) atomicAdd(dst + j, v[j]);
-                        } else if (nco == 16 && (((P.f32_cstride | (P.f32_coff + co0)) & 3) == 0)) {
+                        if (nco == 16 && (((P.f32_cstride | (P.f32_coff + co0)) & 3) == 0)) {
                             if (P.f32_accumulate) {
                                 float4 old[4];
 #pragma unroll
@@ -438,7 +428,6 @@ extern "C" int n3d_conv_gemm(const N3DConvGemm* p, void* stream) {
     N3D_CHECK_ARG(p->Cout >= 1 && p->N >= 1 && p->MH >= 1 && p->MW >= 1, "n3d_conv_gemm: bad sizes");
     N3D_CHECK_ARG(((uintptr_t)p->a_hi & 15) == 0 && ((uintptr_t)p->w_hi & 15) == 0, "n3d_conv_gemm: operands must be 16-byte aligned");
     N3D_CHECK_ARG(p->mode == 0 || (p->mode == 1 && p->out_f32), "n3d_conv_gemm: bad mode");
-    N3D_CHECK_ARG(p->ksplit <= 1 || (p->mode == 1 && !p->f32_nchw), "n3d_conv_gemm: split-K needs mode 1 (raw NHWC fp32 accumulation into a zeroed buffer)");
     cudaStream_t st = (cudaStream_t)stream;
 
     KParams K;
@@ -461,8 +450,7 @@ extern "C" int n3d_conv_gemm(const N3DConvGemm* p, void* stream) {
             bn = cands[i];
             break;
         }
-        const int want_split = p->ksplit > 1 ? p->ksplit : 1;
-        while (bn > (want_split > 1 ? 128 : 32) && tiles_m * n3d_div_up(p->Cout, bn) * want_split < 148) bn = (bn == 96) ? 32 : bn / 2;
+        while (bn > 32 && tiles_m * n3d_div_up(p->Cout, bn) < 148) bn = (bn == 96) ? 32 : bn / 2;
     }
     K.block_n = bn;
     K.tiles_n = n3d_div_up(p->Cout, bn);
@@ -474,12 +462,6 @@ extern "C" int n3d_conv_gemm(const N3DConvGemm* p, void* stream) {
     K.stage_bytes = 2 * K.a_bytes + 2 * K.b_bytes;
     K.stages = min(6, (200 * 1024) / K.stage_bytes);      // + 8 KiB epilogue staging + barriers + 1 KiB alignment slack <= 227 KiB
     K.cin_chunks = n3d_div_up(p->Cin, K.block_k);
-    {
-        const int ksteps = p->ntaps * K.cin_chunks;
-        int want = p->ksplit > 1 ? min(p->ksplit, ksteps) : 1;
-        K.ksteps_per_split = n3d_div_up(ksteps, want);
-        K.ksplit = n3d_div_up(ksteps, K.ksteps_per_split);      // no empty splits
-    }
     K.ntaps = p->ntaps; K.nprod = p->nprod; K.a_img_stride = p->a_img_mul;
     for (int i = 0; i < p->ntaps; ++i) {
         K.taps[i] = p->taps[i];
@@ -518,7 +500,7 @@ extern "C" int n3d_conv_gemm(const N3DConvGemm* p, void* stream) {
         }
         smem_configured = 227 * 1024;
     }
-    const int total_tiles = tiles_m * K.tiles_n * K.ksplit;
+    const int total_tiles = tiles_m * K.tiles_n;
     static int num_sms = 0;
     if (!num_sms) {
         int dev = 0;

@@ -181,21 +181,6 @@ __global__ void __launch_bounds__(256) fir_up_epilogue_kernel(const float* __res
     }
 }
 
-// pointwise epilogue of a raw (mode 1 / split-K) conv output
-__global__ void __launch_bounds__(256) pointwise_epilogue_kernel(const float* __restrict__ raw, int N, int H, int W, int C, EpiParams E) {
-    const int c4n = C >> 2;
-    const int64_t total = (int64_t)N * H * W * c4n;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int c4 = (int)(i % c4n);
-        int64_t t = i / c4n;
-        const int x = (int)(t % W); t /= W;
-        const int y = (int)(t % H);
-        const int n = (int)(t / H);
-        const float4 v = __ldg(reinterpret_cast<const float4*>(raw) + i);
-        epi_store(E, v, n, y, x, H, W, C, c4 * 4);
-    }
-}
-
 // FIR (pad 2,2,2,2) -> [(H+1),(W+1)] -> parity-split bf16 hi/lo, layout [4 parities][N][SH][SW][C].
 // thread = (sub-pixel (sy,sx), 4-channel group) -> the 2x2 block of FIR outputs (2sy+a, 2sx+b), one per parity image; separable
 // row streaming as above (25 loads per 4 outputs).
@@ -379,22 +364,6 @@ extern "C" int n3d_fir_up_epilogue(const float* raw, int N, int H2, int W2, int 
     const int64_t total = (int64_t)N * (H2 / 2) * (W2 / 2) * (C / 4);
     fir_up_epilogue_kernel<<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(raw, N, H2, W2, C, E);
     N3D_CHECK_LAUNCH("n3d_fir_up_epilogue");
-    return N3D_OK;
-}
-
-extern "C" int n3d_epilogue(const float* raw, int N, int H, int W, int C, const float* dcoef, const float* bias, const float* noise,
-                            int64_t noise_nstride, float gain, float slope, float clamp, const N3DSplitOut out[2], float* out_f32,
-                            int f32_cstride, int f32_coff, void* stream) {
-    N3D_CHECK_ARG(raw && out, "n3d_epilogue: null pointer");
-    N3D_CHECK_ARG(C % 4 == 0, "n3d_epilogue: C must be a multiple of 4");
-    EpiParams E;
-    E.dcoef = dcoef; E.bias = bias; E.noise = noise; E.noise_nstride = noise_nstride; E.gain = gain; E.slope = slope; E.clamp = clamp;
-    E.out[0] = out[0]; E.out[1] = out[1]; E.out_f32 = out_f32; E.f32_cstride = f32_cstride; E.f32_coff = f32_coff;
-    for (int k = 0; k < 2; ++k)
-        N3D_CHECK_ARG(!E.out[k].hi || ((E.out[k].cstride % 4 == 0) && (E.out[k].coff % 4 == 0)), "n3d_epilogue: unaligned split output");
-    N3D_CHECK_ARG(!out_f32 || (f32_cstride % 4 == 0 && f32_coff % 4 == 0), "n3d_epilogue: unaligned fp32 output");
-    pointwise_epilogue_kernel<<<grid_for((int64_t)N * H * W * (C / 4), 256, 16), 256, 0, (cudaStream_t)stream>>>(raw, N, H, W, C, E);
-    N3D_CHECK_LAUNCH("n3d_epilogue");
     return N3D_OK;
 }
 

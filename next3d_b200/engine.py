@@ -218,15 +218,6 @@ class Engine:
         e1.record()
         self.prof.append((kind, e0, e1, flops, info))
 
-    @staticmethod
-    def _ksplit(N, MH, MW, cin, cout, ntaps):
-        """Split-K factor for layers too small to fill the 148 SMs with (pixel tile x channel tile) work items alone."""
-        base = -(-N * MH * MW // 128) * -(-cout // 128)
-        if base >= 100:
-            return 1
-        ksteps = ntaps * -(-cin // 64)
-        return max(1, min(16, -(-256 // base), ksteps // 2))
-
     def _gemm(self, a_hi, a_lo, w_hi, w_lo, taps, N, MH, MW, **kw):
         """n3d_conv_gemm + bookkeeping: algorithmic FLOPs = 2 * Cin * Cout * taps * M-space positions (one product)."""
         flops = 2.0 * a_hi.shape[-1] * w_hi.shape[1] * len(taps) * N * MH * MW
@@ -275,32 +266,17 @@ class Engine:
         noise, nstride = self._noise(L, noise_mode)
         clamp = L.clamp if L.clamp is not None else -1.0
         if L.up == 1:
-            ks = self._ksplit(N, res_in, res_in, L.cin, L.cout, 9)
-            if ks > 1:                                     # small layer: split-K partial sums into a zeroed raw buffer + pointwise epilogue
-                raw = torch.zeros(N, res_in, res_in, L.cout, dtype=torch.float32, device=self.device)
-                self._gemm(a.hi, a.lo, L.w_hi, L.w_lo, K.taps_conv3x3(), N, res_in, res_in, nprod=self.nprod, ksplit=ks, mode=1, out_f32=raw,
-                           f32_cstride=L.cout)
-                K.epilogue(raw, self._dcoef(L), L.bias, noise, SQRT2, 0.2, clamp, outs=outs, out_f32=f32,
-                           f32_cstride=L.cout if f32 is not None else 0, noise_nstride=nstride)
-                self.launches += 3
-                return
             self._gemm(a.hi, a.lo, L.w_hi, L.w_lo, K.taps_conv3x3(), N, res_in, res_in, nprod=self.nprod, dcoef=self._dcoef(L), bias=L.bias,
                         noise=noise, noise_nstride=nstride, gain=SQRT2, slope=0.2, clamp=clamp, outs=outs, out_f32=f32,
                         f32_cstride=L.cout if f32 is not None else 0)
             self.launches += 1
             return
-        ks = self._ksplit(N, res_in + 1, res_in + 1, L.cin, L.cout, 2)
-        if ks > 1:
-            raw = torch.zeros(N, 2 * res_in + 1, 2 * res_in + 1, L.cout, dtype=torch.float32, device=self.device)
-            self.launches += 1
-        else:
-            raw = self._f32(N, 2 * res_in + 1, 2 * res_in + 1, L.cout)
+        raw = self._f32(N, 2 * res_in + 1, 2 * res_in + 1, L.cout)
         for pa in (0, 1):
             for pb in (0, 1):
-                taps = K.taps_transposed(pa, pb)
-                self._gemm(a.hi, a.lo, L.w_hi, L.w_lo, taps, N, res_in + 1 - pa, res_in + 1 - pb, nprod=self.nprod,
-                            ksplit=min(ks, max(1, len(taps) * -(-L.cin // 64) // 2)), mode=1, out_f32=raw, f32_cstride=L.cout, oy_mul=2, oy_off=pa,
-                            ox_mul=2, ox_off=pb, OH=2 * res_in + 1, OW=2 * res_in + 1)
+                self._gemm(a.hi, a.lo, L.w_hi, L.w_lo, K.taps_transposed(pa, pb), N, res_in + 1 - pa, res_in + 1 - pb, nprod=self.nprod,
+                            mode=1, out_f32=raw, f32_cstride=L.cout, oy_mul=2, oy_off=pa, ox_mul=2, ox_off=pb, OH=2 * res_in + 1,
+                            OW=2 * res_in + 1)
         K.fir_up_epilogue(raw, L.cout, self._dcoef(L), L.bias, noise, SQRT2, 0.2, clamp, outs=outs, out_f32=f32,
                           f32_cstride=L.cout if f32 is not None else 0, noise_nstride=nstride)
         self.launches += 5
@@ -318,16 +294,6 @@ class Engine:
         L, N = self.plain[name], self._N
         self._cur_layer = name
         gain, slope = (SQRT2, 0.2) if act == 'lrelu' else (1.0, 1.0)
-        mres = res // 2 if stride2 else res
-        ks = self._ksplit(N, mres, mres, L.cin, L.cout, L.k * L.k) if not accumulate else 1
-        if ks > 1:
-            raw = torch.zeros(N, mres, mres, L.cout, dtype=torch.float32, device=self.device)
-            taps = K.taps_stride2() if stride2 else (K.taps_conv3x3() if L.k == 3 else K.taps_conv1x1())
-            self._gemm(a.hi, a.lo, L.w_hi, L.w_lo, taps, N, mres, mres, a_img_mul=N if stride2 else 0, nprod=self.nprod, ksplit=ks, mode=1,
-                       out_f32=raw, f32_cstride=L.cout)
-            K.epilogue(raw, None, L.bias, None, gain, slope, -1.0, outs=outs, out_f32=f32, f32_cstride=L.cout if f32 is not None else 0)
-            self.launches += 3
-            return
         if stride2:
             self._gemm(a.hi, a.lo, L.w_hi, L.w_lo, K.taps_stride2(), N, res // 2, res // 2, a_img_mul=N, nprod=self.nprod, bias=L.bias, gain=gain,
                         slope=slope, outs=outs, out_f32=f32, f32_cstride=L.cout if f32 is not None else 0, f32_accumulate=accumulate)

@@ -52,7 +52,7 @@ def make_split_out(hi=None, lo=None, style=None, cstride=0, coff=0):
 
 
 # ------------------------------------------------------------------------------------------------ kernels
-def conv_gemm(a_hi, a_lo, w_hi, w_lo, taps, N, MH, MW, *, a_img_mul=0, nprod=3, ksplit=1, mode=0, dcoef=None, bias=None, noise=None,
+def conv_gemm(a_hi, a_lo, w_hi, w_lo, taps, N, MH, MW, *, a_img_mul=0, nprod=3, mode=0, dcoef=None, bias=None, noise=None,
               noise_nstride=0, gain=1.0, slope=1.0, clamp=-1.0, outs=(), out_f32=None, f32_cstride=0, f32_coff=0, f32_nchw=False,
               f32_accumulate=False, oy_mul=1, oy_off=0, ox_mul=1, ox_off=0, OH=None, OW=None):
     """a_*: bf16 [NI, AH, AW, Cin]; w_*: bf16 [T, Cout, Cin]; taps: list of (dy, dx, img_off, wtap)."""
@@ -68,7 +68,7 @@ def conv_gemm(a_hi, a_lo, w_hi, w_lo, taps, N, MH, MW, *, a_img_mul=0, nprod=3, 
     p.ntaps = len(taps)
     for i, (dy, dx, io, wt) in enumerate(taps):
         p.taps[i] = _lib.ConvTap(dy, dx, io, wt)
-    p.nprod, p.ksplit, p.mode = nprod, ksplit, mode
+    p.nprod, p.mode = nprod, mode
     p.dcoef, p.bias, p.noise, p.noise_nstride = ptr(dcoef), ptr(bias), ptr(noise), noise_nstride
     p.gain, p.slope, p.clamp = gain, slope, clamp
     for i, o in enumerate(outs):
@@ -95,15 +95,6 @@ def fir_up_epilogue(raw, C_, dcoef, bias, noise, gain, slope, clamp, outs=(), ou
         arr[i] = o
     check(lib.n3d_fir_up_epilogue(ptr(raw), N, RH - 1, RW - 1, C_, ptr(dcoef), ptr(bias), ptr(noise), noise_nstride, gain, slope, clamp, arr,
                                   ptr(out_f32), f32_cstride, f32_coff, stream_ptr()), 'n3d_fir_up_epilogue')
-
-
-def epilogue(raw, dcoef, bias, noise, gain, slope, clamp, outs=(), out_f32=None, f32_cstride=0, f32_coff=0, noise_nstride=0):
-    N, H, W, Cc = raw.shape
-    arr = (_lib.SplitOut * 2)()
-    for i, o in enumerate(outs):
-        arr[i] = o
-    check(lib.n3d_epilogue(ptr(raw), N, H, W, Cc, ptr(dcoef), ptr(bias), ptr(noise), noise_nstride, gain, slope, clamp, arr, ptr(out_f32),
-                           f32_cstride, f32_coff, stream_ptr()), 'n3d_epilogue')
 
 
 def fir_down_split(x, hi, lo):

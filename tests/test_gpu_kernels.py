@@ -54,28 +54,6 @@ def test_conv3x3_plain(K, N, Cin, Cout, res):
     assert range_rel_err(got, ref) < 6e-5
 
 
-@pytest.mark.parametrize('N,Cin,Cout,res,ks', [(8, 512, 512, 4, 16), (2, 512, 512, 8, 8), (1, 1024, 512, 16, 5), (1, 64, 96, 8, 3)])
-def test_conv_split_k(K, N, Cin, Cout, res, ks):
-    """Split-K: partial sums reduced with atomics into a zeroed raw buffer, then the pointwise epilogue kernel."""
-    g = _g(91 + res)
-    x = torch.randn(N, Cin, res, res, generator=g)
-    w = torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(Cin * 9)
-    b = torch.randn(Cout, generator=g)
-    d = torch.rand(N, Cout, generator=g) + 0.5
-    y = F.leaky_relu(F.conv2d(x.double(), w.double(), padding=1).float() * d[:, :, None, None] + b[None, :, None, None], 0.2) * math.sqrt(2)
-    a_hi, a_lo = _nhwc_split(K, x)
-    w_hi, w_lo = K.pack_conv_weight(w.to(DEV))
-    raw = torch.zeros(N, res, res, Cout, device=DEV)
-    K.conv_gemm(a_hi, a_lo, w_hi, w_lo, K.taps_conv3x3(), N, res, res, ksplit=ks, mode=1, out_f32=raw, f32_cstride=Cout)
-    out = torch.zeros(N, res, res, Cout, device=DEV)
-    hi = torch.zeros(N, res, res, Cout, device=DEV, dtype=torch.bfloat16)
-    lo = torch.zeros_like(hi)
-    dd, bd = d.to(DEV), b.to(DEV)
-    K.epilogue(raw, dd, bd, None, math.sqrt(2), 0.2, -1.0, outs=[K.make_split_out(hi, lo, None, Cout, 0)], out_f32=out, f32_cstride=Cout)
-    assert range_rel_err(out.permute(0, 3, 1, 2).cpu(), y) < 6e-5
-    assert range_rel_err(_join(hi, lo).permute(0, 3, 1, 2).cpu(), y) < 8e-5
-
-
 def test_conv_single_product_is_bf16_grade(K):
     g = _g(7)
     x = torch.randn(1, 64, 16, 16, generator=g)
