@@ -16,6 +16,8 @@ def init_from_env(backend=None):
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     if world > 1 and not dist.is_initialized():
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', ''):
+            os.environ['NCCL_DEBUG'] = 'WARN'      # keep rank 0's stdout to the single JSON line (NCCL prints its banner to stdout)
         backend = backend or ('nccl' if torch.cuda.is_available() else 'gloo')
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         if backend == 'nccl':
