@@ -163,9 +163,10 @@ int n3d_transform_points(const float* pts, int N, int P, const float* rot, int n
 /* pytorch3d-semantics rasterizer (oracle/oracle_c.c is the bit-exact CPU statement) -- replaces
  * pytorch3d.renderer.mesh.rasterize_meshes as called at volumetric_rendering/renderer.py:414-424 (blur 0, 1 face/pixel,
  * cull_backfaces, no perspective correction).  verts [NM, V, 3] NDC fp32, faces [F,3] int32 (shared by all images)
- * -> pix_to_face [NM,H,W] int32 (face id or -1), bary [NM,H,W,3] fp32 (-1 where empty). */
+ * -> pix_to_face [NM,H,W] int32 (face id or -1), bary [NM,H,W,3] fp32 (-1 where empty).
+ * workspace: caller-provided, 16-byte aligned, NM * F * 16 floats (per-face setup records shared by all pixel bins). */
 int n3d_rasterize(const float* verts, const int32_t* faces, int NM, int V, int F, int H, int W, int32_t* pix_to_face,
-                  float* bary, void* stream);
+                  float* bary, float* workspace, void* stream);
 
 /* Texture lookup for the 4 rendered views of each sample (triplane_next3d.py:211-228, renderer.py:425-437):
  *   uv = sum_k bary_k * face_uv[f,k,:] (0 where nothing is visible); value = bilinear(texture[n], uv) (grid_sample, zeros

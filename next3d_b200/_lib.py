@@ -71,7 +71,7 @@ _SIGNATURES = {
     'n3d_upsample2d_nhwc': ([P, C.c_int, C.c_int, C.c_int, C.c_int, P, C.c_int, P], C.c_int),
     'n3d_downsample2d_nhwc': ([P, C.c_int, C.c_int, C.c_int, C.c_int, P, P], C.c_int),
     'n3d_transform_points': ([P, C.c_int, C.c_int, P, C.c_int, F32, C.c_int, P, P], C.c_int),
-    'n3d_rasterize': ([P, P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, P, P, P], C.c_int),
+    'n3d_rasterize': ([P, P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, P, P, P, P], C.c_int),
     'n3d_uv_sample': ([P, P, P, P, P] + [C.c_int] * 8 + [P, P, P], C.c_int),
     'n3d_fill_mouth': ([P, C.c_int, C.c_int, C.c_int, P], C.c_int),
     'n3d_mouth_box': ([P, C.c_int, P, P], C.c_int),

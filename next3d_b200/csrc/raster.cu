@@ -56,17 +56,53 @@ __device__ __forceinline__ float edge_fn(float px, float py, float ax, float ay,
 
 constexpr int kBin = 16;
 constexpr int kChunk = 256;
+constexpr int kSetupFloats = 16;     // per (image, face) workspace record: bbox (xmin,xmax,ymin,ymax) | x0 y0 z0 x1 y1 z1 x2 y2 z2 area | pad
 
-__global__ void __launch_bounds__(256) rasterize_kernel(const float* __restrict__ verts, const int* __restrict__ faces, int V, int F, int H,
-                                                        int W, int* __restrict__ pix_to_face, float* __restrict__ bary) {
+// Pass 1: one thread per (image, face): culling + bounding box + barycentric denominator exactly as oracle_c.c, stored once
+// instead of being recomputed by every 16x16-pixel bin.  Culled faces get an empty bbox (xmin = +inf).
+__global__ void __launch_bounds__(256) raster_setup_kernel(const float* __restrict__ verts, const int* __restrict__ faces, int NM, int V, int F,
+                                                           float* __restrict__ ws) {
+    const int64_t total = (int64_t)NM * F;
+    const float kEps = 1e-8f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int f = (int)(i % F);
+        const int img = (int)(i / F);
+        const float* vb = verts + (int64_t)img * V * 3;
+        const int i0 = faces[f * 3 + 0], i1 = faces[f * 3 + 1], i2 = faces[f * 3 + 2];
+        FaceSetup s;
+        s.x0 = vb[i0 * 3]; s.y0 = vb[i0 * 3 + 1]; s.z0 = vb[i0 * 3 + 2];
+        s.x1 = vb[i1 * 3]; s.y1 = vb[i1 * 3 + 1]; s.z1 = vb[i1 * 3 + 2];
+        s.x2 = vb[i2 * 3]; s.y2 = vb[i2 * 3 + 1]; s.z2 = vb[i2 * 3 + 2];
+        s.xmin = fminf(s.x0, fminf(s.x1, s.x2)); s.xmax = fmaxf(s.x0, fmaxf(s.x1, s.x2));
+        s.ymin = fminf(s.y0, fminf(s.y1, s.y2)); s.ymax = fmaxf(s.y0, fmaxf(s.y1, s.y2));
+        const float zmax = fmaxf(s.z0, fmaxf(s.z1, s.z2));
+        const float face_area = edge_fn(s.x0, s.y0, s.x1, s.y1, s.x2, s.y2);
+        bool keep = !(zmax < 0.f);
+        keep = keep && !(face_area <= kEps && face_area >= -kEps);
+        keep = keep && !(face_area < 0.f);
+        s.area = __fadd_rn(edge_fn(s.x2, s.y2, s.x0, s.y0, s.x1, s.y1), kEps);
+        float4* o = reinterpret_cast<float4*>(ws + i * kSetupFloats);
+        o[0] = keep ? make_float4(s.xmin, s.xmax, s.ymin, s.ymax) : make_float4(INFINITY, -INFINITY, INFINITY, -INFINITY);
+        o[1] = make_float4(s.x0, s.y0, s.z0, s.x1);
+        o[2] = make_float4(s.y1, s.z1, s.x2, s.y2);
+        o[3] = make_float4(s.z2, s.area, 0.f, 0.f);
+    }
+}
+
+// Pass 2: one CTA per 16x16-pixel bin of one image, one thread per pixel.  Face records stream through in chunks of 256: each
+// thread tests one face's bbox against the bin (one coalesced float4), survivors are compacted into shared memory (order-free),
+// then every pixel thread tests the survivors.  The nearest hit wins; equal depth keeps the lower face index (explicit
+// tie-break, so the result does not depend on processing order).  All fp32 arithmetic uses round-to-nearest intrinsics in the
+// oracle's expression order (no FMA contraction) -> bit-identical index buffers and barycentrics.
+__global__ void __launch_bounds__(256) rasterize_kernel(const float* __restrict__ ws, int F, int H, int W, int* __restrict__ pix_to_face,
+                                                        float* __restrict__ bary) {
     __shared__ FaceSetup sf[kChunk];
     __shared__ int s_count;
     const int bins_x = (W + kBin - 1) / kBin;
     const int img = blockIdx.y;
     const int bx = blockIdx.x % bins_x, by = blockIdx.x / bins_x;
     const int xi = bx * kBin + (threadIdx.x % kBin), yi = by * kBin + (threadIdx.x / kBin);
-    const float* vb = verts + (int64_t)img * V * 3;
-    const float kEps = 1e-8f;
+    const float* wb = ws + (int64_t)img * F * kSetupFloats;
 
     const float xf = __fadd_rn(-1.f, __fdiv_rn(__fadd_rn(__fmul_rn(2.f, (float)(W - 1 - xi)), 1.f), (float)W));
     const float yf = __fadd_rn(-1.f, __fdiv_rn(__fadd_rn(__fmul_rn(2.f, (float)(H - 1 - yi)), 1.f), (float)H));
@@ -85,22 +121,15 @@ __global__ void __launch_bounds__(256) rasterize_kernel(const float* __restrict_
         __syncthreads();
         const int f = f0 + threadIdx.x;
         if (f < F) {
-            const int i0 = faces[f * 3 + 0], i1 = faces[f * 3 + 1], i2 = faces[f * 3 + 2];
-            FaceSetup s;
-            s.x0 = vb[i0 * 3]; s.y0 = vb[i0 * 3 + 1]; s.z0 = vb[i0 * 3 + 2];
-            s.x1 = vb[i1 * 3]; s.y1 = vb[i1 * 3 + 1]; s.z1 = vb[i1 * 3 + 2];
-            s.x2 = vb[i2 * 3]; s.y2 = vb[i2 * 3 + 1]; s.z2 = vb[i2 * 3 + 2];
-            s.xmin = fminf(s.x0, fminf(s.x1, s.x2)); s.xmax = fmaxf(s.x0, fmaxf(s.x1, s.x2));
-            s.ymin = fminf(s.y0, fminf(s.y1, s.y2)); s.ymax = fmaxf(s.y0, fmaxf(s.y1, s.y2));
-            const float zmax = fmaxf(s.z0, fmaxf(s.z1, s.z2));
-            const float face_area = edge_fn(s.x0, s.y0, s.x1, s.y1, s.x2, s.y2);
-            bool keep = !(zmax < 0.f);
-            keep = keep && !(face_area <= kEps && face_area >= -kEps);
-            keep = keep && !(face_area < 0.f);
-            keep = keep && !(s.xmax < bin_xmin || s.xmin > bin_xmax || s.ymax < bin_ymin || s.ymin > bin_ymax);
-            if (keep) {
-                s.area = __fadd_rn(edge_fn(s.x2, s.y2, s.x0, s.y0, s.x1, s.y1), kEps);
-                s.id = f;
+            const float4* rec = reinterpret_cast<const float4*>(wb + (int64_t)f * kSetupFloats);
+            const float4 bb = __ldg(rec);
+            if (!(bb.y < bin_xmin || bb.x > bin_xmax || bb.w < bin_ymin || bb.z > bin_ymax)) {     // also false for culled faces
+                const float4 r1 = __ldg(rec + 1), r2 = __ldg(rec + 2), r3 = __ldg(rec + 3);
+                FaceSetup s;
+                s.xmin = bb.x; s.xmax = bb.y; s.ymin = bb.z; s.ymax = bb.w;
+                s.x0 = r1.x; s.y0 = r1.y; s.z0 = r1.z; s.x1 = r1.w;
+                s.y1 = r2.x; s.z1 = r2.y; s.x2 = r2.z; s.y2 = r2.w;
+                s.z2 = r3.x; s.area = r3.y; s.id = f;
                 sf[atomicAdd(&s_count, 1)] = s;
             }
         }
@@ -208,33 +237,36 @@ __global__ void __launch_bounds__(256) uv_sample_kernel(const int* __restrict__ 
 __global__ void __launch_bounds__(1024) fill_mouth_kernel(float* __restrict__ alpha, int H, int W) {
     extern __shared__ unsigned char st[];
     __shared__ int s_changed;
+    const int SW = W + 4;                  // row pitch in bytes: (W+4)/4 is odd -> row sweeps (one thread per row) are bank-conflict free
     float* a = alpha + (int64_t)blockIdx.x * H * W;
     const float seed = __fmul_rn(a[0], 255.f);
     const float vmin = seed, vmax = __fadd_rn(seed, 254.f);
     for (int i = threadIdx.x; i < H * W; i += blockDim.x) {
         const float v = __fmul_rn(a[i], 255.f);
-        st[i] = (v >= vmin && v <= vmax) ? 1 : 0;
+        st[(i / W) * SW + (i % W)] = (v >= vmin && v <= vmax) ? 1 : 0;
     }
     __syncthreads();
     if (threadIdx.x == 0) st[0] = 2;      // the seed pixel itself is always filled
     __syncthreads();
+    // Four sweep directions run concurrently on disjoint thread groups (state only ever goes 1 -> 2, byte stores: benign races
+    // merely delay propagation to the next pass); repeat until a pass changes nothing.
+    const int group = threadIdx.x >> 8, gi = threadIdx.x & 255;
     for (int iter = 0; iter < 4 * (H + W); ++iter) {
         if (threadIdx.x == 0) s_changed = 0;
         __syncthreads();
         int changed = 0;
-        for (int y = threadIdx.x; y < H; y += blockDim.x) {          // rows
-            unsigned char* r = st + y * W;
-            bool reach = false;
-            for (int x = 0; x < W; ++x) { const unsigned char s = r[x]; if (s == 0) reach = false; else if (s == 2) reach = true; else if (reach) { r[x] = 2; changed = 1; } }
-            reach = false;
-            for (int x = W - 1; x >= 0; --x) { const unsigned char s = r[x]; if (s == 0) reach = false; else if (s == 2) reach = true; else if (reach) { r[x] = 2; changed = 1; } }
-        }
-        __syncthreads();
-        for (int x = threadIdx.x; x < W; x += blockDim.x) {          // columns
-            bool reach = false;
-            for (int y = 0; y < H; ++y) { const unsigned char s = st[y * W + x]; if (s == 0) reach = false; else if (s == 2) reach = true; else if (reach) { st[y * W + x] = 2; changed = 1; } }
-            reach = false;
-            for (int y = H - 1; y >= 0; --y) { const unsigned char s = st[y * W + x]; if (s == 0) reach = false; else if (s == 2) reach = true; else if (reach) { st[y * W + x] = 2; changed = 1; } }
+        if (group == 0) {
+            for (int y = gi; y < H; y += 256) { unsigned char* r = st + y * SW; bool reach = false;
+                for (int x = 0; x < W; ++x) { const unsigned char s = r[x]; if (s == 0) reach = false; else if (s == 2) reach = true; else if (reach) { r[x] = 2; changed = 1; } } }
+        } else if (group == 1) {
+            for (int y = gi; y < H; y += 256) { unsigned char* r = st + y * SW; bool reach = false;
+                for (int x = W - 1; x >= 0; --x) { const unsigned char s = r[x]; if (s == 0) reach = false; else if (s == 2) reach = true; else if (reach) { r[x] = 2; changed = 1; } } }
+        } else if (group == 2) {
+            for (int x = gi; x < W; x += 256) { bool reach = false;
+                for (int y = 0; y < H; ++y) { const unsigned char s = st[y * SW + x]; if (s == 0) reach = false; else if (s == 2) reach = true; else if (reach) { st[y * SW + x] = 2; changed = 1; } } }
+        } else {
+            for (int x = gi; x < W; x += 256) { bool reach = false;
+                for (int y = H - 1; y >= 0; --y) { const unsigned char s = st[y * SW + x]; if (s == 0) reach = false; else if (s == 2) reach = true; else if (reach) { st[y * SW + x] = 2; changed = 1; } } }
         }
         if (changed) atomicOr(&s_changed, 1);
         __syncthreads();
@@ -244,7 +276,7 @@ __global__ void __launch_bounds__(1024) fill_mouth_kernel(float* __restrict__ al
     }
     for (int i = threadIdx.x; i < H * W; i += blockDim.x) {
         const float al = a[i];
-        const float filled = st[i] == 2 ? 255.f : __fmul_rn(al, 255.f);
+        const float filled = st[(i / W) * SW + (i % W)] == 2 ? 255.f : __fmul_rn(al, 255.f);
         const float m = __fsub_rn(__fdiv_rn(filled, 127.5f), 1.f);
         const float t = __fdiv_rn(__fadd_rn(__fmul_rn(__fsub_rn(__fmul_rn(m, 2.f), 1.f), -1.f), 1.f), 2.f);
         a[i] = fminf(fmaxf(__fadd_rn(al, t), 0.f), 1.f);
@@ -371,11 +403,13 @@ extern "C" int n3d_transform_points(const float* pts, int N, int P, const float*
 }
 
 extern "C" int n3d_rasterize(const float* verts, const int32_t* faces, int NM, int V, int F, int H, int W, int32_t* pix_to_face,
-                             float* bary, void* stream) {
-    N3D_CHECK_ARG(verts && faces && pix_to_face && bary && NM > 0 && F > 0 && H > 0 && W > 0, "n3d_rasterize: bad args");
+                             float* bary, float* workspace, void* stream) {
+    N3D_CHECK_ARG(verts && faces && pix_to_face && bary && workspace && NM > 0 && F > 0 && H > 0 && W > 0, "n3d_rasterize: bad args");
     N3D_CHECK_ARG(NM <= 65535, "n3d_rasterize: too many images (%d)", NM);
+    N3D_CHECK_ARG(((uintptr_t)workspace & 15) == 0, "n3d_rasterize: workspace must be 16-byte aligned");
+    raster_setup_kernel<<<grid_for((int64_t)NM * F, 256), 256, 0, (cudaStream_t)stream>>>(verts, faces, NM, V, F, workspace);
     dim3 grid(((W + kBin - 1) / kBin) * ((H + kBin - 1) / kBin), NM);
-    rasterize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(verts, faces, V, F, H, W, pix_to_face, bary);
+    rasterize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(workspace, F, H, W, pix_to_face, bary);
     N3D_CHECK_LAUNCH("n3d_rasterize");
     return N3D_OK;
 }
@@ -393,7 +427,7 @@ extern "C" int n3d_uv_sample(const int32_t* pix_to_face, const float* bary, cons
 
 extern "C" int n3d_fill_mouth(float* alpha, int NI, int H, int W, void* stream) {
     N3D_CHECK_ARG(alpha && NI > 0 && H > 0 && W > 0, "n3d_fill_mouth: bad args");
-    N3D_CHECK_ARG((int64_t)H * W <= 200 * 1024, "n3d_fill_mouth: image %dx%d too large for the shared-memory state map", H, W);
+    N3D_CHECK_ARG((int64_t)H * (W + 4) <= 200 * 1024, "n3d_fill_mouth: image %dx%d too large for the shared-memory state map", H, W);
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(fill_mouth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
@@ -402,7 +436,7 @@ extern "C" int n3d_fill_mouth(float* alpha, int NI, int H, int W, void* stream) 
         }
         configured = true;
     }
-    fill_mouth_kernel<<<NI, 1024, (size_t)H * W, (cudaStream_t)stream>>>(alpha, H, W);
+    fill_mouth_kernel<<<NI, 1024, (size_t)H * (W + 4), (cudaStream_t)stream>>>(alpha, H, W);
     N3D_CHECK_LAUNCH("n3d_fill_mouth");
     return N3D_OK;
 }

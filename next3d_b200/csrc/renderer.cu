@@ -31,7 +31,10 @@ struct RenderK {
 };
 
 __device__ __forceinline__ float softplus_t(float x) { return x > 20.f ? x : log1pf(expf(x)); }   // torch Softplus(beta 1, threshold 20)
-__device__ __forceinline__ float sigmoid_t(float x) { return 1.f / (1.f + expf(-x)); }
+// MUFU-based variants for the 96 activations per decoded sample (ex2.approx / lg2.approx / rcp.approx): absolute error ~1e-7 on
+// O(1) values, far inside the 2e-5 kernel tolerance; the few per-ray compositing transcendentals keep the exact versions.
+__device__ __forceinline__ float softplus_fast(float x) { return x > 20.f ? x : __logf(1.f + __expf(x)); }
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 
 __device__ __forceinline__ float hash_uniform(uint64_t seed, uint64_t idx) {
     uint64_t z = seed + idx * 0x9E3779B97F4A7C15ull;
@@ -102,7 +105,7 @@ __device__ __forceinline__ void decode_row(float* __restrict__ row, const float*
             const float4 wv = w[c4];
             a += wv.x * f[c4 * 4] + wv.y * f[c4 * 4 + 1] + wv.z * f[c4 * 4 + 2] + wv.w * f[c4 * 4 + 3];
         }
-        const float h = softplus_t(a);
+        const float h = softplus_fast(a);
         const float4* w1 = reinterpret_cast<const float4*>(sW1t + j * kW1Stride);
 #pragma unroll
         for (int o4 = 0; o4 < kW1Stride / 4; ++o4) {
@@ -111,7 +114,7 @@ __device__ __forceinline__ void decode_row(float* __restrict__ row, const float*
         }
     }
 #pragma unroll
-    for (int c = 0; c < kFeat; ++c) row[c] = sigmoid_t(o[1 + c]) * 1.002f - 0.001f;
+    for (int c = 0; c < kFeat; ++c) row[c] = sigmoid_fast(o[1 + c]) * 1.002f - 0.001f;
     row[32] = o[0];
 }
 

@@ -132,9 +132,12 @@ def transform_points(pts, rot, zoff, ndc_flip, out):
           'n3d_transform_points')
 
 
-def rasterize(verts, faces, H, W, p2f, bary):
+def rasterize(verts, faces, H, W, p2f, bary, workspace=None):
     NM, V, _ = verts.shape
-    check(lib.n3d_rasterize(ptr(verts), ptr(faces), NM, V, faces.shape[0], H, W, ptr(p2f), ptr(bary), stream_ptr()), 'n3d_rasterize')
+    if workspace is None:
+        workspace = torch.empty(NM * faces.shape[0] * 16, dtype=torch.float32, device=verts.device)
+    check(lib.n3d_rasterize(ptr(verts), ptr(faces), NM, V, faces.shape[0], H, W, ptr(p2f), ptr(bary), ptr(workspace), stream_ptr()),
+          'n3d_rasterize')
 
 
 def uv_sample(p2f, bary, face_uv, texture, eye_mask, tex_planes, alpha):
