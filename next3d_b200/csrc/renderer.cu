@@ -50,41 +50,41 @@ __device__ __forceinline__ float linspace_at(float start, float end, int steps, 
     return i < steps / 2 ? start + step * (float)i : end - step * (float)(steps - 1 - i);
 }
 
-// Bilinear tap setup for one plane at grid coords (gx, gy) (grid_sample: zeros padding, align_corners=False).  Out-of-range
-// taps get weight 0 and a clamped (always valid) address so that all loads can be issued unconditionally and together.
-struct Taps { const float* p[4]; float w[4]; };
-__device__ __forceinline__ Taps plane_taps(const float* __restrict__ plane, int PH, int PW, float gx, float gy, int lane) {
+// Tri-plane feature of one sample, computed by a whole warp (lanes = the 32 channels).
+// The 12 bilinear taps (3 planes x 4 corners; plane 0 <- (x,y), 1 <- (x,z), 2 <- (z,y); grid_sample with zeros padding,
+// align_corners=False) are set up ONCE per sample by lanes 0..11 -- lane l owns plane l/4, corner l%4 and computes that tap's
+// element offset (clamped, always valid) and weight (0 when out of range) -- and then broadcast with shuffles, instead of every
+// lane redundantly running the whole address/weight arithmetic.  All 12 loads (each one coalesced 128-byte line) are issued
+// before any is consumed.  Returns ((f0 + f1) + f2) / 3 like sampled_features.mean(1).
+__device__ __forceinline__ float triplane_feature(const float* __restrict__ planes_n, int PH, int PW, float px, float py, float pz, float scale, int lane) {
+    const int plane = (lane >> 2) % 3, corner = lane & 3;
+    const float x = scale * px, y = scale * py, z = scale * pz;
+    const float gx = plane == 2 ? z : x;
+    const float gy = plane == 1 ? z : y;
     const float ix = ((gx + 1.f) * (float)PW - 1.f) * 0.5f, iy = ((gy + 1.f) * (float)PH - 1.f) * 0.5f;
     const float flx = floorf(ix), fly = floorf(iy);
-    const int x0 = (int)flx, y0 = (int)fly;
-    const float fx = ix - flx, fy = iy - fly;
-    const bool xin0 = x0 >= 0 && x0 < PW, xin1 = x0 + 1 >= 0 && x0 + 1 < PW;
-    const bool yin0 = y0 >= 0 && y0 < PH, yin1 = y0 + 1 >= 0 && y0 + 1 < PH;
-    const int xc0 = min(max(x0, 0), PW - 1), xc1 = min(max(x0 + 1, 0), PW - 1);
-    const int yc0 = min(max(y0, 0), PH - 1), yc1 = min(max(y0 + 1, 0), PH - 1);
-    Taps t;
-    t.p[0] = plane + ((int64_t)yc0 * PW + xc0) * kFeat + lane; t.w[0] = (xin0 && yin0) ? (1.f - fx) * (1.f - fy) : 0.f;
-    t.p[1] = plane + ((int64_t)yc0 * PW + xc1) * kFeat + lane; t.w[1] = (xin1 && yin0) ? fx * (1.f - fy) : 0.f;
-    t.p[2] = plane + ((int64_t)yc1 * PW + xc0) * kFeat + lane; t.w[2] = (xin0 && yin1) ? (1.f - fx) * fy : 0.f;
-    t.p[3] = plane + ((int64_t)yc1 * PW + xc1) * kFeat + lane; t.w[3] = (xin1 && yin1) ? fx * fy : 0.f;
-    return t;
-}
-
-// mean over the three planes of the bilinear features at world point (px,py,pz); plane 0 <- (x,y), 1 <- (x,z), 2 <- (z,y).
-// The 12 loads (each one coalesced 128-byte line across the warp) are issued back to back before any is consumed.
-__device__ __forceinline__ float triplane_feature(const float* __restrict__ planes_n, int PH, int PW, float px, float py, float pz, float scale, int lane) {
-    const float x = scale * px, y = scale * py, z = scale * pz;
-    const int64_t ps = (int64_t)PH * PW * kFeat;
-    const Taps t0 = plane_taps(planes_n, PH, PW, x, y, lane);
-    const Taps t1 = plane_taps(planes_n + ps, PH, PW, x, z, lane);
-    const Taps t2 = plane_taps(planes_n + 2 * ps, PH, PW, z, y, lane);
-    float v0[4], v1[4], v2[4];
+    const int xi = (int)flx + (corner & 1), yi = (int)fly + (corner >> 1);
+    const float wx = (corner & 1) ? ix - flx : 1.f - (ix - flx);
+    const float wy = (corner >> 1) ? iy - fly : 1.f - (iy - fly);
+    const bool inside = xi >= 0 && xi < PW && yi >= 0 && yi < PH;
+    const float my_w = inside ? wx * wy : 0.f;
+    const int my_off = ((plane * PH + min(max(yi, 0), PH - 1)) * PW + min(max(xi, 0), PW - 1)) * kFeat;
+    float v[12], w[12];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { v0[i] = __ldg(t0.p[i]); v1[i] = __ldg(t1.p[i]); v2[i] = __ldg(t2.p[i]); }
-    float f0 = 0.f, f1 = 0.f, f2 = 0.f;
+    for (int i = 0; i < 12; ++i) {
+        const int off = __shfl_sync(0xffffffffu, my_off, i);
+        w[i] = __shfl_sync(0xffffffffu, my_w, i);
+        v[i] = __ldg(planes_n + off + lane);
+    }
+    float f[3];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { f0 += t0.w[i] * v0[i]; f1 += t1.w[i] * v1[i]; f2 += t2.w[i] * v2[i]; }
-    return ((f0 + f1) + f2) / 3.f;
+    for (int p = 0; p < 3; ++p) {
+        float a = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) a += w[p * 4 + c] * v[p * 4 + c];
+        f[p] = a;
+    }
+    return ((f[0] + f[1]) + f[2]) / 3.f;
 }
 
 // decode one sample in place: row[0..31] features -> row[0..31] rgb, row[32] sigma

@@ -503,7 +503,7 @@ class Engine:
         boxes = torch.empty(N, 4, dtype=torch.int32, device=dev)
         lm2d = tl[:, 0, :, :2].contiguous()
         K.mouth_box(lm2d, boxes)
-        self.launches += 6
+        self.launches += 7                                                          # rasterize = setup pass + bin pass
         # mouth crop -> StyleUNet -> paste back -> neural blending
         front = tex_planes[0]
         crop = self._f32(N, 64, 64, cfg.plane_ch)
