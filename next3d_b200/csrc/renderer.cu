@@ -12,6 +12,7 @@
 //   rank-counting sort-merge, colour accumulation) runs one warp per ray.
 #include "common.cuh"
 #include "../../include/next3d_b200.h"
+#include <stdlib.h>
 
 namespace {
 
@@ -74,7 +75,7 @@ __device__ __forceinline__ float triplane_feature(const float* __restrict__ plan
     for (int i = 0; i < 12; ++i) {
         const int off = __shfl_sync(0xffffffffu, my_off, i);
         w[i] = __shfl_sync(0xffffffffu, my_w, i);
-        v[i] = __ldg(planes_n + off + lane);
+        v[i] = __ldg(planes_n + (unsigned)(off + lane));
     }
     float f[3];
 #pragma unroll
@@ -103,7 +104,7 @@ __device__ __forceinline__ void decode_row(float* __restrict__ row, const float*
 #pragma unroll
         for (int c4 = 0; c4 < kFeat / 4; ++c4) {
             const float4 wv = w[c4];
-            a += wv.x * f[c4 * 4] + wv.y * f[c4 * 4 + 1] + wv.z * f[c4 * 4 + 2] + wv.w * f[c4 * 4 + 3];
+            a = fmaf(wv.x, f[c4 * 4], a); a = fmaf(wv.y, f[c4 * 4 + 1], a); a = fmaf(wv.z, f[c4 * 4 + 2], a); a = fmaf(wv.w, f[c4 * 4 + 3], a);
         }
         const float h = softplus_fast(a);
         const float4* w1 = reinterpret_cast<const float4*>(sW1t + j * kW1Stride);
@@ -217,6 +218,8 @@ __global__ void __launch_bounds__(kMaxThreads) render_kernel(const RenderK K) {
             r[0] = o[0]; r[1] = o[1]; r[2] = o[2];
             r[3] = wv[0] / nrm; r[4] = wv[1] / nrm; r[5] = wv[2] / nrm;
         }
+        // sample index -> image of this ray (tail rays of the last CTA reuse the last valid ray; their results are never stored)
+        sRay[tid * 8 + 6] = __int_as_float((int)(min(gr, total_rays - 1) / K.M));
     }
     // ---- coarse depths (renderer.py:203-205)
     for (int s = tid; s < R * Dc; s += blockDim.x) {
@@ -235,14 +238,17 @@ __global__ void __launch_bounds__(kMaxThreads) render_kernel(const RenderK K) {
     const int64_t plane_img = (int64_t)3 * P.PH * P.PW * kFeat;
 
     // ---- coarse pass: gather (warp per sample) then decode (thread per sample)
+    {
+        int r = warp / Dc, k = warp - r * Dc;                  // sample s = r * Dc + k, advanced without divisions
 #pragma unroll 2
-    for (int s = warp; s < R * Dc; s += nwarps) {
-        const int r = s / Dc;
-        const int64_t gr = min(ray0 + r, total_rays - 1);        // tail rays recompute the last valid ray (never stored)
-        const float* ry = sRay + r * 8;
-        const float t = sTc[s];
-        sC[s * kRowStride + lane] = triplane_feature(P.planes + (gr / K.M) * plane_img, P.PH, P.PW, ry[0] + t * ry[3], ry[1] + t * ry[4],
-                                                     ry[2] + t * ry[5], scale, lane);
+        for (int s = warp; s < R * Dc; s += nwarps) {
+            const float* ry = sRay + r * 8;
+            const float t = sTc[s];
+            sC[s * kRowStride + lane] = triplane_feature(P.planes + (int64_t)__float_as_int(ry[6]) * plane_img, P.PH, P.PW, ry[0] + t * ry[3],
+                                                         ry[1] + t * ry[4], ry[2] + t * ry[5], scale, lane);
+            k += nwarps;
+            while (k >= Dc) { k -= Dc; ++r; }
+        }
     }
     __syncthreads();
     for (int s = tid; s < R * Dc; s += blockDim.x) decode_row(sC + s * kRowStride, sW0, sB0, sW1t, sB1);
@@ -304,14 +310,17 @@ __global__ void __launch_bounds__(kMaxThreads) render_kernel(const RenderK K) {
     __syncthreads();
 
     // ---- fine pass
+    {
+        int r = warp / Df, k = warp - r * Df;
 #pragma unroll 2
-    for (int s = warp; s < R * Df; s += nwarps) {
-        const int r = s / Df;
-        const int64_t gr = min(ray0 + r, total_rays - 1);
-        const float* ry = sRay + r * 8;
-        const float t = sTf[s];
-        sF[s * kRowStride + lane] = triplane_feature(P.planes + (gr / K.M) * plane_img, P.PH, P.PW, ry[0] + t * ry[3], ry[1] + t * ry[4],
-                                                     ry[2] + t * ry[5], scale, lane);
+        for (int s = warp; s < R * Df; s += nwarps) {
+            const float* ry = sRay + r * 8;
+            const float t = sTf[s];
+            sF[s * kRowStride + lane] = triplane_feature(P.planes + (int64_t)__float_as_int(ry[6]) * plane_img, P.PH, P.PW, ry[0] + t * ry[3],
+                                                         ry[1] + t * ry[4], ry[2] + t * ry[5], scale, lane);
+            k += nwarps;
+            while (k >= Df) { k -= Df; ++r; }
+        }
     }
     __syncthreads();
     for (int s = tid; s < R * Df; s += blockDim.x) decode_row(sF + s * kRowStride, sW0, sB0, sW1t, sB1);
@@ -457,7 +466,13 @@ extern "C" int n3d_render_rays(const N3DRender* p, void* stream) {
     K.p = *p;
     K.M = p->res * p->res;
     const int dmax = p->depth_coarse > p->depth_fine ? p->depth_coarse : p->depth_fine;
-    K.rays_per_cta = kMaxThreads / dmax;
+    static int target_threads = 0;
+    if (!target_threads) {
+        const char* e = getenv("N3D_RENDER_THREADS");          // tuning knob: threads (= rays x samples) per CTA
+        target_threads = e ? atoi(e) : kMaxThreads;
+        if (target_threads < 32 || target_threads > kMaxThreads) target_threads = kMaxThreads;
+    }
+    K.rays_per_cta = target_threads / dmax;
     if (K.rays_per_cta < 1) K.rays_per_cta = 1;
     K.delta_coarse = (float)(((double)p->ray_end - (double)p->ray_start) / (double)(p->depth_coarse - 1));
     const int threads = ((K.rays_per_cta * dmax + 31) / 32) * 32;
