@@ -127,6 +127,14 @@ typedef struct {
 
 int n3d_conv_gemm(const N3DConvGemm* p, void* stream);
 
+/* Stride-2 transposed 3x3 convolution (the first half of every up-sampling conv: conv_transpose2d(stride 2),
+ * conv2d_resample.py:114-127) as ONE launch of the same kernel: the four output-parity classes
+ *   out[2p+a, 2q+b] = sum_{ky = a (mod 2), kx = b (mod 2)} W[ky,kx] x[p - (ky-a)/2, q - (kx-b)/2]
+ * are four sub-problems (4/2/2/1 taps) scheduled together.  p->MH, p->MW = INPUT height / width, p->T must be 9; the raw fp32
+ * NHWC result [N, 2H+1, 2W+1, Cout] is written to p->out_f32 (f32_cstride / f32_coff honoured); taps, offsets, OH/OW, mode and
+ * the epilogue fields of the descriptor are ignored (follow with n3d_fir_up_epilogue). */
+int n3d_conv_transposed_gemm(const N3DConvGemm* p, void* stream);
+
 /* fp32 NHWC -> split bf16 NHWC with optional per-(n,c) modulation: out = split(x[n,y,x,c] * style[n,c]). */
 int n3d_modulate_split(const float* x, int64_t npix_per_img, int N, int C, const float* style, void* hi, void* lo,
                        int out_cstride, int out_coff, void* stream);

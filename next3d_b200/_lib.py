@@ -65,6 +65,7 @@ _SIGNATURES = {
     'n3d_styles': ([P, C.c_int, C.c_int, C.c_int, P, P, P, P, P, P, P, C.c_int, P], C.c_int),
     'n3d_demod': ([P, P, P, P, P, P, P, P, C.c_int, C.c_int, P], C.c_int),
     'n3d_conv_gemm': ([C.POINTER(ConvGemm), P], C.c_int),
+    'n3d_conv_transposed_gemm': ([C.POINTER(ConvGemm), P], C.c_int),
     'n3d_modulate_split': ([P, I64, C.c_int, C.c_int, P, P, P, C.c_int, C.c_int, P], C.c_int),
     'n3d_fir_up_epilogue': ([P, C.c_int, C.c_int, C.c_int, C.c_int, P, P, P, I64, F32, F32, F32, C.POINTER(SplitOut), P, C.c_int, C.c_int, P], C.c_int),
     'n3d_fir_down_split': ([P, C.c_int, C.c_int, C.c_int, C.c_int, P, P, P], C.c_int),

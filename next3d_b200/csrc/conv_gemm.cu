@@ -30,7 +30,10 @@ struct KParams {
     CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
     int N, MH, MW, Cout;
     int TW, TH, TN;                  // TW*TH*TN == 128, all powers of two
-    int tiles_x, tiles_y, tiles_i, tiles_n;
+    int tiles_i, tiles_n;
+    // up to 4 sub-problems sharing operands / tile shape / epilogue (the 4 output-parity classes of a stride-2 transposed conv)
+    int nsub;
+    struct Sub { int tap_begin, ntaps, MH, MW, tiles_x, tiles_y, oy_off, ox_off, tile_end; } sub[4];
     int block_n, acc_stride, tmem_cols, stages, stage_bytes, b_bytes, a_bytes, block_k;
     int cin_chunks, ntaps, nprod, a_img_stride;
     N3DConvTap taps[9];
@@ -39,7 +42,7 @@ struct KParams {
     float gain, slope, clamp;
     N3DSplitOut out[2];
     float* out_f32; int f32_cstride, f32_coff, f32_nchw, f32_accumulate;
-    int oy_mul, oy_off, ox_mul, ox_off, OH, OW;
+    int oy_mul, ox_mul, OH, OW;
     int* err_flag;
 };
 
@@ -118,6 +121,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+struct TileInfo { int sub, tn, x0, y0, n0; };
+__device__ __forceinline__ TileInfo decode_tile(const KParams& P, int tile) {
+    int sidx = 0, begin = 0;
+    while (sidx + 1 < P.nsub && tile >= P.sub[sidx].tile_end) { begin = P.sub[sidx].tile_end; ++sidx; }
+    const int local = tile - begin;
+    TileInfo t;
+    t.sub = sidx;
+    t.tn = local % P.tiles_n;
+    const int tm = local / P.tiles_n, tx = P.sub[sidx].tiles_x, ty = P.sub[sidx].tiles_y;
+    t.x0 = (tm % tx) * P.TW;
+    t.y0 = ((tm / tx) % ty) * P.TH;
+    t.n0 = (tm / (tx * ty)) * P.TN;
+    return t;
+}
+
 // ---------------------------------------------------------------------------------------------- the kernel
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ KParams P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -153,9 +171,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-    const int tiles_m = P.tiles_x * P.tiles_y * P.tiles_i;
-    const int total_tiles = tiles_m * P.tiles_n;
-    const int ksteps = P.ntaps * P.cin_chunks;
+    const int total_tiles = P.sub[P.nsub - 1].tile_end;
 
     if (warp == 0) {
         // ===================================================== TMA producer
@@ -163,11 +179,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             int s = 0; uint32_t ph = 0;
             const uint32_t tx_bytes = (uint32_t)(P.nprod == 3 ? 2 : 1) * (uint32_t)(P.a_bytes + P.b_bytes);
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int tn = tile % P.tiles_n, tm = tile / P.tiles_n;
-                const int x0 = (tm % P.tiles_x) * P.TW, y0 = ((tm / P.tiles_x) % P.tiles_y) * P.TH;
-                const int n0 = (tm / (P.tiles_x * P.tiles_y)) * P.TN;
-                for (int t = 0; t < P.ntaps; ++t) {
-                    const N3DConvTap tap = P.taps[t];
+                const TileInfo ti = decode_tile(P, tile);
+                const int tn = ti.tn, x0 = ti.x0, y0 = ti.y0, n0 = ti.n0;
+                const int tap_begin = P.sub[ti.sub].tap_begin, ntaps = P.sub[ti.sub].ntaps;
+                for (int t = 0; t < ntaps; ++t) {
+                    const N3DConvTap tap = P.taps[tap_begin + t];
                     for (int kc = 0; kc < P.cin_chunks; ++kc) {
                         mbar_wait(empty_bar(s), ph ^ 1u, P.err_flag, 1);
                         const uint32_t sa = smem_base + (uint32_t)s * (uint32_t)P.stage_bytes;
@@ -195,6 +211,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             const int k16 = P.block_k / 16;
             int s = 0; uint32_t ph = 0; int acc = 0; uint32_t acc_ph = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int ksteps = P.sub[decode_tile(P, tile).sub].ntaps * P.cin_chunks;
                 mbar_wait(tempty_bar(acc), acc_ph ^ 1u, P.err_flag, 2);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P.acc_stride);
@@ -230,12 +247,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         const bool staged = (P.TN == 1) && (P.mode == 0);
         uint32_t acc_ph = 0;
         for (int tile = blockIdx.x + g * gridDim.x; tile < total_tiles; tile += 2 * gridDim.x) {
-            const int tn = tile % P.tiles_n, tm = tile / P.tiles_n;
-            const int x = (tm % P.tiles_x) * P.TW + tw, y = ((tm / P.tiles_x) % P.tiles_y) * P.TH + th;
-            const int n0 = (tm / (P.tiles_x * P.tiles_y)) * P.TN;
+            const TileInfo ti = decode_tile(P, tile);
+            const int tn = ti.tn, n0 = ti.n0;
+            const int x = ti.x0 + tw, y = ti.y0 + th;
             const int n = n0 + tnn;
-            const int oy = y * P.oy_mul + P.oy_off, ox = x * P.ox_mul + P.ox_off;
-            const bool valid = (n < P.N) && (y < P.MH) && (x < P.MW) && (oy < P.OH) && (ox < P.OW);
+            const int oy = y * P.oy_mul + P.sub[ti.sub].oy_off, ox = x * P.ox_mul + P.sub[ti.sub].ox_off;
+            const bool valid = (n < P.N) && (y < P.sub[ti.sub].MH) && (x < P.sub[ti.sub].MW) && (oy < P.OH) && (ox < P.OW);
             const int64_t opix = ((int64_t)n * P.OH + oy) * P.OW + ox;
             float nz = 0.f;
             if (valid && P.noise) nz = __ldg(P.noise + (int64_t)n * P.noise_nstride + (int64_t)oy * P.OW + ox);
@@ -419,25 +436,42 @@ int* g_err_flag = nullptr;   // device int, lazily allocated once per process; o
 
 }  // namespace
 
-extern "C" int n3d_conv_gemm(const N3DConvGemm* p, void* stream) {
+namespace {
+struct SubSpec { int ntaps; N3DConvTap taps[9]; int MH, MW, oy_off, ox_off; };
+
+int launch_conv(const N3DConvGemm* p, int nsub, const SubSpec* specs, void* stream) {
     N3D_CHECK_ARG(p && p->a_hi && p->w_hi, "n3d_conv_gemm: null operand");
     N3D_CHECK_ARG(p->nprod == 1 || p->nprod == 3, "n3d_conv_gemm: nprod must be 1 or 3");
     N3D_CHECK_ARG(p->nprod == 1 || (p->a_lo && p->w_lo), "n3d_conv_gemm: nprod 3 needs lo operands");
-    N3D_CHECK_ARG(p->ntaps >= 1 && p->ntaps <= 9, "n3d_conv_gemm: ntaps %d", p->ntaps);
     N3D_CHECK_ARG(p->Cin >= 8 && p->Cin % 8 == 0, "n3d_conv_gemm: Cin %d must be a multiple of 8 (TMA 16-byte strides)", p->Cin);
-    N3D_CHECK_ARG(p->Cout >= 1 && p->N >= 1 && p->MH >= 1 && p->MW >= 1, "n3d_conv_gemm: bad sizes");
+    N3D_CHECK_ARG(p->Cout >= 1 && p->N >= 1, "n3d_conv_gemm: bad sizes");
     N3D_CHECK_ARG(((uintptr_t)p->a_hi & 15) == 0 && ((uintptr_t)p->w_hi & 15) == 0, "n3d_conv_gemm: operands must be 16-byte aligned");
     N3D_CHECK_ARG(p->mode == 0 || (p->mode == 1 && p->out_f32), "n3d_conv_gemm: bad mode");
     cudaStream_t st = (cudaStream_t)stream;
 
     KParams K;
     memset(&K, 0, sizeof(K));
-    K.N = p->N; K.MH = p->MH; K.MW = p->MW; K.Cout = p->Cout;
-    K.TW = min(16, pow2_ceil(p->MW));
-    K.TH = min(kBlockM / K.TW, pow2_ceil(p->MH));
+    K.N = p->N; K.Cout = p->Cout;
+    int maxH = 1, maxW = 1;
+    for (int i = 0; i < nsub; ++i) { maxH = max(maxH, specs[i].MH); maxW = max(maxW, specs[i].MW); }
+    K.TW = min(16, pow2_ceil(maxW));
+    K.TH = min(kBlockM / K.TW, pow2_ceil(maxH));
     K.TN = kBlockM / (K.TW * K.TH);
-    K.tiles_x = n3d_div_up(p->MW, K.TW); K.tiles_y = n3d_div_up(p->MH, K.TH); K.tiles_i = n3d_div_up(p->N, K.TN);
-    const int tiles_m = K.tiles_x * K.tiles_y * K.tiles_i;
+    K.tiles_i = n3d_div_up(p->N, K.TN);
+    K.nsub = nsub;
+    int tiles_m = 0, tap_total = 0;
+    for (int i = 0; i < nsub; ++i) {
+        N3D_CHECK_ARG(specs[i].ntaps >= 1 && specs[i].MH >= 1 && specs[i].MW >= 1, "n3d_conv_gemm: bad sub-problem %d", i);
+        K.sub[i].tap_begin = tap_total; K.sub[i].ntaps = specs[i].ntaps;
+        for (int t = 0; t < specs[i].ntaps; ++t) {
+            N3D_CHECK_ARG(tap_total < 9, "n3d_conv_gemm: more than 9 taps in total");
+            N3D_CHECK_ARG(specs[i].taps[t].wtap >= 0 && specs[i].taps[t].wtap < p->T, "n3d_conv_gemm: tap weight slab out of range");
+            K.taps[tap_total++] = specs[i].taps[t];
+        }
+        K.sub[i].MH = specs[i].MH; K.sub[i].MW = specs[i].MW; K.sub[i].oy_off = specs[i].oy_off; K.sub[i].ox_off = specs[i].ox_off;
+        K.sub[i].tiles_x = n3d_div_up(specs[i].MW, K.TW); K.sub[i].tiles_y = n3d_div_up(specs[i].MH, K.TH);
+        tiles_m += K.sub[i].tiles_x * K.sub[i].tiles_y * K.tiles_i;
+    }
     // block_n: the largest legal UMMA N (M=128 needs N % 16 == 0) not exceeding Cout, shrunk while the launch would
     // not fill one wave of the 148 SMs.
     const int cout16 = ((p->Cout + 15) / 16) * 16;
@@ -462,17 +496,17 @@ extern "C" int n3d_conv_gemm(const N3DConvGemm* p, void* stream) {
     K.stage_bytes = 2 * K.a_bytes + 2 * K.b_bytes;
     K.stages = min(6, (200 * 1024) / K.stage_bytes);      // + 8 KiB epilogue staging + barriers + 1 KiB alignment slack <= 227 KiB
     K.cin_chunks = n3d_div_up(p->Cin, K.block_k);
-    K.ntaps = p->ntaps; K.nprod = p->nprod; K.a_img_stride = p->a_img_mul;
-    for (int i = 0; i < p->ntaps; ++i) {
-        K.taps[i] = p->taps[i];
-        N3D_CHECK_ARG(p->taps[i].wtap >= 0 && p->taps[i].wtap < p->T, "n3d_conv_gemm: tap %d weight slab out of range", i);
+    K.ntaps = tap_total; K.nprod = p->nprod; K.a_img_stride = p->a_img_mul;
+    {
+        int end = 0;
+        for (int i = 0; i < nsub; ++i) { end += K.sub[i].tiles_x * K.sub[i].tiles_y * K.tiles_i * K.tiles_n; K.sub[i].tile_end = end; }
     }
     K.mode = p->mode; K.dcoef = p->dcoef; K.bias = p->bias; K.noise = p->noise; K.noise_nstride = p->noise_nstride;
     K.gain = p->gain; K.slope = p->slope; K.clamp = p->clamp;
     K.out[0] = p->out[0]; K.out[1] = p->out[1];
     K.out_f32 = p->out_f32; K.f32_cstride = p->f32_cstride; K.f32_coff = p->f32_coff; K.f32_nchw = p->f32_nchw;
     K.f32_accumulate = p->f32_accumulate;
-    K.oy_mul = p->oy_mul; K.oy_off = p->oy_off; K.ox_mul = p->ox_mul; K.ox_off = p->ox_off; K.OH = p->OH; K.OW = p->OW;
+    K.oy_mul = p->oy_mul; K.ox_mul = p->ox_mul; K.OH = p->OH; K.OW = p->OW;
     if (!g_err_flag) {
         if (cudaMalloc(&g_err_flag, sizeof(int)) != cudaSuccess) { n3d_set_error("n3d_conv_gemm: cudaMalloc(err flag) failed"); return N3D_ERR_CUDA; }
         cudaMemset(g_err_flag, 0, sizeof(int));
@@ -512,4 +546,42 @@ extern "C" int n3d_conv_gemm(const N3DConvGemm* p, void* stream) {
     conv_gemm_kernel<<<grid, kThreads, smem, st>>>(K);
     N3D_CHECK_LAUNCH("n3d_conv_gemm");
     return N3D_OK;
+}
+}  // namespace
+
+extern "C" int n3d_conv_gemm(const N3DConvGemm* p, void* stream) {
+    N3D_CHECK_ARG(p, "n3d_conv_gemm: null descriptor");
+    N3D_CHECK_ARG(p->ntaps >= 1 && p->ntaps <= 9, "n3d_conv_gemm: ntaps %d", p->ntaps);
+    N3D_CHECK_ARG(p->MH >= 1 && p->MW >= 1, "n3d_conv_gemm: bad M-space");
+    SubSpec sp;
+    sp.ntaps = p->ntaps;
+    for (int i = 0; i < p->ntaps; ++i) sp.taps[i] = p->taps[i];
+    sp.MH = p->MH; sp.MW = p->MW; sp.oy_off = p->oy_off; sp.ox_off = p->ox_off;
+    return launch_conv(p, 1, &sp, stream);
+}
+
+// Stride-2 transposed 3x3 convolution (conv_transpose2d(stride 2), conv2d_resample.py:114-127) as ONE launch: the four
+// output-parity classes (a, b) -- out[2p+a, 2q+b] = sum_{ky = a mod 2, kx = b mod 2} W[ky,kx] x[p-(ky-a)/2, q-(kx-b)/2] -- become four
+// sub-problems (4 / 2 / 2 / 1 taps) of the same persistent kernel, heaviest first.  p->MH, p->MW = INPUT height/width; the raw fp32
+// result [(2H+1), (2W+1)] goes to p->out_f32 (mode 1); taps / offsets / OH / OW of the descriptor are ignored and derived here.
+extern "C" int n3d_conv_transposed_gemm(const N3DConvGemm* p, void* stream) {
+    N3D_CHECK_ARG(p && p->out_f32, "n3d_conv_transposed_gemm: null descriptor / output");
+    N3D_CHECK_ARG(p->T == 9, "n3d_conv_transposed_gemm: needs 3x3 weights (T == 9)");
+    N3DConvGemm q = *p;
+    q.mode = 1; q.oy_mul = 2; q.ox_mul = 2; q.OH = 2 * p->MH + 1; q.OW = 2 * p->MW + 1; q.a_img_mul = 0;
+    SubSpec sp[4];
+    const int order[4][2] = {{0, 0}, {0, 1}, {1, 0}, {1, 1}};
+    for (int c = 0; c < 4; ++c) {
+        const int a = order[c][0], b = order[c][1];
+        sp[c].ntaps = 0;
+        for (int ky = 0; ky < 3; ++ky)
+            for (int kx = 0; kx < 3; ++kx)
+                if ((ky - a) % 2 == 0 && (kx - b) % 2 == 0) {
+                    N3DConvTap t;
+                    t.dy = (int8_t)(-(ky - a) / 2); t.dx = (int8_t)(-(kx - b) / 2); t.img_off = 0; t.wtap = ky * 3 + kx;
+                    sp[c].taps[sp[c].ntaps++] = t;
+                }
+        sp[c].MH = p->MH + 1 - a; sp[c].MW = p->MW + 1 - b; sp[c].oy_off = a; sp[c].ox_off = b;
+    }
+    return launch_conv(&q, 4, sp, stream);
 }

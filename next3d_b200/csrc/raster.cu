@@ -167,65 +167,69 @@ __device__ __forceinline__ void bilinear_setup(float gx, float gy, int W, int H,
     x0 = (int)flx; y0 = (int)fly; fx = ix - flx; fy = iy - fly;
 }
 
-// one warp per pixel, lanes = channels (C == 32): 4 taps x 128-byte coalesced loads per view
+// One warp per output pixel, lanes = channels for the texture loads.  The per-tap arithmetic (face lookup, barycentric UV,
+// bilinear corner offset + weight) is done ONCE: lane l < 16 owns texture tap (view l/4, corner l%4), lane 16 + l owns the
+// corresponding eye-mask tap; offsets / weights are then broadcast with shuffles and the 16 texture loads (one coalesced
+// 128-byte line each) are issued together.
 __global__ void __launch_bounds__(256) uv_sample_kernel(const int* __restrict__ p2f, const float* __restrict__ bary, const float* __restrict__ face_uv,
                                                         const float* __restrict__ tex, const float* __restrict__ mask, int N, int H, int W, int TH,
                                                         int TW, int C, int MH, int MW, float* __restrict__ planes, float* __restrict__ alpha) {
     const int lane = threadIdx.x & 31;
     const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const int64_t total = (int64_t)N * H * W;
+    const int64_t HW = (int64_t)H * W, total = (int64_t)N * HW;
+    const int view = (lane >> 2) & 3, corner = lane & 3;
+    const bool is_mask = lane >= 16;
+    const int GW = is_mask ? MW : TW, GH = is_mask ? MH : TH;
     for (int64_t pi = warp_global; pi < total; pi += nwarps) {
-        const int n = (int)(pi / ((int64_t)H * W));
-        const int64_t pix = pi % ((int64_t)H * W);
-        float side_acc = 0.f;
-        for (int view = 0; view < 4; ++view) {
-            const int64_t src = ((int64_t)(n * 4 + view) * H * W) + pix;
-            const int f = p2f[src];
-            float u = 0.f, v = 0.f, vis = 0.f;
-            if (f >= 0) {
-                const float b0 = bary[src * 3], b1 = bary[src * 3 + 1], b2 = bary[src * 3 + 2];
-                const float* fu = face_uv + (int64_t)f * 6;
-                u = __fadd_rn(__fadd_rn(__fmul_rn(b0, fu[0]), __fmul_rn(b1, fu[2])), __fmul_rn(b2, fu[4]));
-                v = __fadd_rn(__fadd_rn(__fmul_rn(b0, fu[1]), __fmul_rn(b1, fu[3])), __fmul_rn(b2, fu[5]));
-                vis = 1.f;
-            }
-            int x0, y0; float fx, fy;
-            bilinear_setup(u, v, TW, TH, x0, y0, fx, fy);
-            const float w00 = (1.f - fx) * (1.f - fy), w01 = fx * (1.f - fy), w10 = (1.f - fx) * fy, w11 = fx * fy;
-            const float* tb = tex + (int64_t)n * TH * TW * C;
-            float acc = 0.f;
-            if (lane < C) {
-                if (y0 >= 0 && y0 < TH) {
-                    if (x0 >= 0 && x0 < TW) acc += w00 * __ldg(tb + ((int64_t)y0 * TW + x0) * C + lane);
-                    if (x0 + 1 >= 0 && x0 + 1 < TW) acc += w01 * __ldg(tb + ((int64_t)y0 * TW + x0 + 1) * C + lane);
-                }
-                if (y0 + 1 >= 0 && y0 + 1 < TH) {
-                    if (x0 >= 0 && x0 < TW) acc += w10 * __ldg(tb + ((int64_t)(y0 + 1) * TW + x0) * C + lane);
-                    if (x0 + 1 >= 0 && x0 + 1 < TW) acc += w11 * __ldg(tb + ((int64_t)(y0 + 1) * TW + x0 + 1) * C + lane);
-                }
-            }
-            if (view == 1) { side_acc = acc; }
-            else if (lane < C) {
-                const int plane = view == 0 ? 0 : (view == 2 ? 1 : 2);
-                const float val = view == 2 ? side_acc + acc : acc;
-                planes[(((int64_t)plane * N + n) * H * W + pix) * C + lane] = val;
-            }
-            if (view != 2 && lane == 0) {
-                int mx0, my0; float mfx, mfy;
-                bilinear_setup(u, v, MW, MH, mx0, my0, mfx, mfy);
-                float m = 0.f;
-                if (my0 >= 0 && my0 < MH) {
-                    if (mx0 >= 0 && mx0 < MW) m += (1.f - mfx) * (1.f - mfy) * __ldg(mask + my0 * MW + mx0);
-                    if (mx0 + 1 >= 0 && mx0 + 1 < MW) m += mfx * (1.f - mfy) * __ldg(mask + my0 * MW + mx0 + 1);
-                }
-                if (my0 + 1 >= 0 && my0 + 1 < MH) {
-                    if (mx0 >= 0 && mx0 < MW) m += (1.f - mfx) * mfy * __ldg(mask + (my0 + 1) * MW + mx0);
-                    if (mx0 + 1 >= 0 && mx0 + 1 < MW) m += mfx * mfy * __ldg(mask + (my0 + 1) * MW + mx0 + 1);
-                }
-                const int aplane = view == 0 ? 0 : (view == 1 ? 1 : 2);
-                alpha[((int64_t)aplane * N + n) * H * W + pix] = m * vis;
-            }
+        const int n = (int)(pi / HW);
+        const int64_t pix = pi - (int64_t)n * HW;
+        const int64_t src = ((int64_t)(n * 4 + view)) * HW + pix;
+        const int f = __ldg(p2f + src);
+        float u = 0.f, v = 0.f;
+        if (f >= 0) {
+            const float b0 = __ldg(bary + src * 3), b1 = __ldg(bary + src * 3 + 1), b2 = __ldg(bary + src * 3 + 2);
+            const float* fu = face_uv + (int64_t)f * 6;
+            u = __fadd_rn(__fadd_rn(__fmul_rn(b0, __ldg(fu)), __fmul_rn(b1, __ldg(fu + 2))), __fmul_rn(b2, __ldg(fu + 4)));
+            v = __fadd_rn(__fadd_rn(__fmul_rn(b0, __ldg(fu + 1)), __fmul_rn(b1, __ldg(fu + 3))), __fmul_rn(b2, __ldg(fu + 5)));
+        }
+        int x0, y0; float fx, fy;
+        bilinear_setup(u, v, GW, GH, x0, y0, fx, fy);
+        const int xi = x0 + (corner & 1), yi = y0 + (corner >> 1);
+        const float wx = (corner & 1) ? fx : 1.f - fx, wy = (corner >> 1) ? fy : 1.f - fy;
+        const bool inside = xi >= 0 && xi < GW && yi >= 0 && yi < GH;
+        const float my_w = inside ? wx * wy : 0.f;
+        const int cy = min(max(yi, 0), GH - 1), cx = min(max(xi, 0), GW - 1);
+        const int my_off = is_mask ? cy * GW + cx : (cy * GW + cx) * C;
+        // ---- eye mask: lanes 16..31 fetch their tap, reduce the 4 corners of each view, alpha = mask * visible
+        float m = is_mask ? my_w * __ldg(mask + my_off) : 0.f;
+        m += __shfl_xor_sync(0xffffffffu, m, 1);
+        m += __shfl_xor_sync(0xffffffffu, m, 2);
+        if (is_mask && corner == 0 && view != 2) {
+            const int aplane = view == 0 ? 0 : (view == 1 ? 1 : 2);
+            alpha[((int64_t)aplane * N + n) * HW + pix] = m * (f >= 0 ? 1.f : 0.f);
+        }
+        // ---- texture: 16 taps broadcast from lanes 0..15
+        const float* tb = tex + (int64_t)n * TH * TW * C;
+        float val[16], wgt[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int off = __shfl_sync(0xffffffffu, my_off, i);
+            wgt[i] = __shfl_sync(0xffffffffu, my_w, i);
+            val[i] = lane < C ? __ldg(tb + (unsigned)(off + lane)) : 0.f;
+        }
+        float acc[4];
+#pragma unroll
+        for (int vw = 0; vw < 4; ++vw) {
+            float a = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) a += wgt[vw * 4 + c] * val[vw * 4 + c];
+            acc[vw] = a;
+        }
+        if (lane < C) {
+            planes[(((int64_t)0 * N + n) * HW + pix) * C + lane] = acc[0];
+            planes[(((int64_t)1 * N + n) * HW + pix) * C + lane] = acc[1] + acc[2];
+            planes[(((int64_t)2 * N + n) * HW + pix) * C + lane] = acc[3];
         }
     }
 }

@@ -272,14 +272,14 @@ class Engine:
             self.launches += 1
             return
         raw = self._f32(N, 2 * res_in + 1, 2 * res_in + 1, L.cout)
-        for pa in (0, 1):
-            for pb in (0, 1):
-                self._gemm(a.hi, a.lo, L.w_hi, L.w_lo, K.taps_transposed(pa, pb), N, res_in + 1 - pa, res_in + 1 - pb, nprod=self.nprod,
-                            mode=1, out_f32=raw, f32_cstride=L.cout, oy_mul=2, oy_off=pa, ox_mul=2, ox_off=pb, OH=2 * res_in + 1,
-                            OW=2 * res_in + 1)
+        flops = 2.0 * L.cin * L.cout * N * (3 * res_in + 2) ** 2          # taps x positions summed over the 4 parity classes
+        self.conv_flops += flops
+        ev = self._prof_begin()
+        K.conv_transposed_gemm(a.hi, a.lo, L.w_hi, L.w_lo, N, res_in, res_in, raw, nprod=self.nprod)
+        self._prof_end(ev, 'conv_gemm', flops, (name, L.cin, L.cout, res_in + 1, res_in + 1, 9))
         K.fir_up_epilogue(raw, L.cout, self._dcoef(L), L.bias, noise, SQRT2, 0.2, clamp, outs=outs, out_f32=f32,
                           f32_cstride=L.cout if f32 is not None else 0, noise_nstride=nstride)
-        self.launches += 5
+        self.launches += 2
 
     def _torgb(self, name, a, res, img, accumulate, nchw=False):
         """ToRGBLayer (networks_stylegan2.py:353-357): 1x1 modulated conv without demodulation, linear bias (+ clamp)."""

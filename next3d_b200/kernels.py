@@ -81,6 +81,22 @@ def conv_gemm(a_hi, a_lo, w_hi, w_lo, taps, N, MH, MW, *, a_img_mul=0, nprod=3, 
     check(lib.n3d_conv_gemm(C.byref(p), stream_ptr()), 'n3d_conv_gemm')
 
 
+def conv_transposed_gemm(a_hi, a_lo, w_hi, w_lo, N, H, W, raw, nprod=3):
+    """Stride-2 transposed 3x3 conv of a [N,H,W,Cin] split activation -> raw fp32 [N,2H+1,2W+1,Cout] (one launch, 4 parity classes)."""
+    NI, AH, AW, Cin = a_hi.shape
+    T, Cout, _ = w_hi.shape
+    p = _lib.ConvGemm()
+    p.a_hi, p.a_lo = ptr(a_hi), ptr(a_lo)
+    p.NI, p.AH, p.AW, p.Cin = NI, AH, AW, Cin
+    p.w_hi, p.w_lo = ptr(w_hi), ptr(w_lo)
+    p.T, p.Cout = T, Cout
+    p.N, p.MH, p.MW = N, H, W
+    p.nprod = nprod
+    p.gain, p.slope, p.clamp = 1.0, 1.0, -1.0
+    p.out_f32, p.f32_cstride = ptr(raw), raw.shape[-1]
+    check(lib.n3d_conv_transposed_gemm(C.byref(p), stream_ptr()), 'n3d_conv_transposed_gemm')
+
+
 def modulate_split(x, style, hi, lo, cstride=None, coff=0):
     """x fp32 NHWC [N,H,W,C]; style [N,C] or None -> hi/lo bf16 (written at channel offset `coff`, stride `cstride`)."""
     N, H, W, Cc = x.shape

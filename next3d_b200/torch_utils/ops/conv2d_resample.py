@@ -53,10 +53,7 @@ def _one_group(x, w, f, up, down, flip_weight):
     K.modulate_split(xn, None, a_hi, a_lo)
     if up == 2 and k == 3:
         raw = torch.empty(N, 2 * H + 1, 2 * W + 1, Cout, device=dev)
-        for pa in (0, 1):
-            for pb in (0, 1):
-                K.conv_gemm(a_hi, a_lo, w_hi, w_lo, K.taps_transposed(pa, pb), N, H + 1 - pa, W + 1 - pb, mode=1, out_f32=raw, f32_cstride=Cout,
-                            oy_mul=2, oy_off=pa, ox_mul=2, ox_off=pb, OH=2 * H + 1, OW=2 * W + 1)
+        K.conv_transposed_gemm(a_hi, a_lo, w_hi, w_lo, N, H, W, raw)
         out = torch.empty(N, 2 * H, 2 * W, Cout, device=dev)
         K.fir_up_epilogue(raw, Cout, None, None, None, 1.0, 1.0, -1.0, out_f32=out, f32_cstride=Cout)
         return out.permute(0, 3, 1, 2)

@@ -130,10 +130,13 @@ def test_upconv_modulated(K, N, Cin, Cout, res):
     a_hi, a_lo = _nhwc_split(K, x * s[:, :, None, None])
     w_hi, w_lo = K.pack_conv_weight(w.to(DEV))
     raw = torch.full((N, 2 * res + 1, 2 * res + 1, Cout), float('nan'), device=DEV)
-    for a in (0, 1):
+    for a in (0, 1):                      # the four parity classes as separate launches ...
         for bb in (0, 1):
             K.conv_gemm(a_hi, a_lo, w_hi, w_lo, K.taps_transposed(a, bb), N, res + 1 - a, res + 1 - bb, mode=1, out_f32=raw,
                         f32_cstride=Cout, oy_mul=2, oy_off=a, ox_mul=2, ox_off=bb, OH=2 * res + 1, OW=2 * res + 1)
+    raw1 = torch.full_like(raw, float('nan'))
+    K.conv_transposed_gemm(a_hi, a_lo, w_hi, w_lo, N, res, res, raw1)        # ... and as one multi-class launch
+    assert torch.equal(raw, raw1)
     assert not torch.isnan(raw).any()
     out = torch.zeros(N, 2 * res, 2 * res, Cout, device=DEV)
     K.fir_up_epilogue(raw, Cout, d.to(DEV), b.to(DEV), nz.to(DEV), math.sqrt(2), 0.2, -1.0, out_f32=out, f32_cstride=Cout)
