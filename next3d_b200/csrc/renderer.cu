@@ -5,7 +5,7 @@
 // (triplane_next3d.py:359-371) and MipRayMarcher2.run_forward (ray_marcher.py:27-66), which materialise
 // [N,3,M*D,32] feature tensors (604 MB per pass at batch 8) in the reference.
 //
-// v1 organisation (SIMT fp32, exact-math transcendental functions):
+// Organisation (see the comment above render_kernel; run_model on arbitrary points keeps the SIMT decoder below):
 //   CTA = RAYS rays x D samples = up to 192 threads.  Gather: one warp per sample, lanes = the 32 channels, so each of the
 //   12 bilinear taps is one coalesced 128-byte line of the channels-last planes.  Decode: one thread per sample, weights
 //   broadcast from shared memory as float4.  Per-ray work (compositing weights via a warp product scan, CDF build + inversion,
@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "../../include/next3d_b200.h"
 #include <stdlib.h>
+#include "tc_ptx.cuh"
 
 namespace {
 
@@ -166,32 +167,99 @@ __device__ __forceinline__ float warp_march_weights(int cnt, const float* __rest
     return warp_sum_f(wsum);
 }
 
-__global__ void __launch_bounds__(kMaxThreads) render_kernel(const RenderK K) {
-    extern __shared__ __align__(16) float smem[];
+// ---------------------------------------------------------------------------------------------------------------------
+// render_kernel: one CTA = R rays x D samples (<= 128 decoded samples per pass = one UMMA M tile), 256 threads.
+//   gather   : warp per sample, lanes = channels; the tri-plane feature is written straight into the K-major SWIZZLE_64B
+//              bf16 (hi, lo) A-operand tile of layer 1;
+//   decoder  : tcgen05.mma, bf16x3 (hi*hi + hi*lo + lo*hi), fp32 accumulators in TMEM:
+//                layer 1  [128 x 32] x [32 x 64]  -> TMEM cols 0..63   (6 MMAs, N = 64)
+//                epilogue 1: + b0, softplus, split -> A tile of layer 2 (SWIZZLE_128B) written by the row's thread
+//                layer 2  [128 x 64] x [64 x 48]  -> TMEM cols 64..111 (12 MMAs, N = 48, 33 used)
+//                epilogue 2: + b1, sigma / sigmoid colours -> fp32 rows [33] in shared memory;
+//   per ray  : one warp per ray (weights by warp scans, inverse-CDF sampling, rank-counting sort-merge, compositing).
+// Operand tiles are written with ordinary shared-memory stores using the same XOR swizzle TMA would apply
+// (16-byte chunk index ^ row bits), then fence.proxy.async + barrier before the single MMA-issuing thread runs.
+constexpr int kRThreads = 256;
+constexpr int kTileRows = 128;
+constexpr int kN2 = 48;                                   // layer-2 UMMA N (33 outputs padded to a multiple of 16)
+
+__device__ __forceinline__ uint32_t sw64_off(int row, int byte_in_row) {       // 64-byte rows, Swizzle<2,4,3>
+    return (uint32_t)(row * 64 + ((((byte_in_row >> 4) ^ ((row >> 1) & 3)) << 4) | (byte_in_row & 15)));
+}
+__device__ __forceinline__ uint32_t sw128_off(int row, int byte_in_row) {      // 128-byte rows, Swizzle<3,4,3>
+    return (uint32_t)(row * 128 + ((((byte_in_row >> 4) ^ (row & 7)) << 4) | (byte_in_row & 15)));
+}
+
+__global__ void __launch_bounds__(kRThreads, 2) render_kernel(const RenderK K) {
+    using namespace n3d_tc;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
     const N3DRender& P = K.p;
     const int Dc = P.depth_coarse, Df = P.depth_fine, R = K.rays_per_cta;
     const int Dt = Dc + Df;
-    // ---- shared memory carve-up
-    float* sW0 = smem;                                   // [64][32]
-    float* sW1t = sW0 + kHidden * kFeat;                 // [64][36]
-    float* sB0 = sW1t + kHidden * kW1Stride;             // [64]
-    float* sB1 = sB0 + kHidden;                          // [36]
-    float* sC = sB1 + kW1Stride;                         // coarse rows [R*Dc][33]
+    // ---- shared memory carve-up: operand tiles first (1024-byte aligned), then fp32 scratch
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* opF_hi = base;                               // [128][32] bf16, 64-B rows   (8 KiB)
+    uint8_t* opF_lo = opF_hi + kTileRows * 64;
+    uint8_t* opH_hi = opF_lo + kTileRows * 64;            // [128][64] bf16, 128-B rows  (16 KiB)
+    uint8_t* opH_lo = opH_hi + kTileRows * 128;
+    uint8_t* opW0_hi = opH_lo + kTileRows * 128;          // [64][32] bf16 (4 KiB)
+    uint8_t* opW0_lo = opW0_hi + kHidden * 64;
+    uint8_t* opW1_hi = opW0_lo + kHidden * 64;            // [48][64] bf16 (6 KiB)
+    uint8_t* opW1_lo = opW1_hi + kN2 * 128;
+    float* sB0 = reinterpret_cast<float*>(opW1_lo + kN2 * 128);   // [64]
+    float* sB1 = sB0 + kHidden;                          // [48]
+    float* sC = sB1 + kN2;                               // coarse rows [R*Dc][33]
     float* sF = sC + R * Dc * kRowStride;                // fine rows   [R*Df][33]
     float* sTc = sF + R * Df * kRowStride;               // coarse depths [R][Dc]
     float* sTf = sTc + R * Dc;                           // fine depths   [R][Df]
     float* sWgt = sTf + R * Df;                          // weights [R][Dt]
     float* sScr = sWgt + R * Dt;                         // per-ray scratch [R][3*Dt]: sorted depths | sorted sigmas | cdf
-    float* sRay = sScr + R * 3 * Dt;                     // [R][8]: origin xyz, dir xyz
+    float* sRay = sScr + R * 3 * Dt;                     // [R][8]: origin xyz, dir xyz, image index
     unsigned char* sOrd = reinterpret_cast<unsigned char*>(sRay + R * 8);   // [R][Dt] merged order
-    __shared__ float s_min[kMaxThreads / 32], s_max[kMaxThreads / 32];
+    __shared__ float s_min[kRThreads / 32], s_max[kRThreads / 32];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_tmem;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const uint64_t seed = P.seed_ptr ? (P.seed + __ldg(reinterpret_cast<const unsigned long long*>(P.seed_ptr))) : P.seed;
     const int64_t ray0 = (int64_t)blockIdx.x * R;        // global ray index = n*M + m
     const int64_t total_rays = (int64_t)P.N * K.M;
+    const uint32_t bar = smem_u32(&s_bar);
 
-    load_decoder(P.w0, P.b0, P.w1, P.b1, sW0, sB0, sW1t, sB1);
+    // ---- one-time setup: mbarrier, TMEM (128 columns), decoder weights -> bf16 (hi, lo) B-operand tiles
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(128u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = tid; i < kHidden * kFeat; i += blockDim.x) {             // W0 [64][32] (row = hidden unit n, K = 32)
+        const int n = i / kFeat, k = i - n * kFeat;
+        __nv_bfloat16 h, l;
+        split_bf16(__ldg(P.w0 + i), h, l);
+        *reinterpret_cast<__nv_bfloat16*>(opW0_hi + sw64_off(n, k * 2)) = h;
+        *reinterpret_cast<__nv_bfloat16*>(opW0_lo + sw64_off(n, k * 2)) = l;
+    }
+    for (int i = tid; i < kN2 * kHidden; i += blockDim.x) {               // W1 [48][64] (rows >= 33 are zero)
+        const int n = i / kHidden, k = i - n * kHidden;
+        __nv_bfloat16 h, l;
+        split_bf16(n < kOut ? __ldg(P.w1 + n * kHidden + k) : 0.f, h, l);
+        *reinterpret_cast<__nv_bfloat16*>(opW1_hi + sw128_off(n, k * 2)) = h;
+        *reinterpret_cast<__nv_bfloat16*>(opW1_lo + sw128_off(n, k * 2)) = l;
+    }
+    for (int i = tid; i < kHidden; i += blockDim.x) sB0[i] = __ldg(P.b0 + i);
+    for (int i = tid; i < kN2; i += blockDim.x) sB1[i] = i < kOut ? __ldg(P.b1 + i) : 0.f;
+    // rows of the A tiles that no sample maps to are still multiplied: keep them finite
+    for (int i = tid; i < (kTileRows * 64) / 16; i += blockDim.x) {
+        reinterpret_cast<uint4*>(opF_hi)[i] = make_uint4(0, 0, 0, 0);
+        reinterpret_cast<uint4*>(opF_lo)[i] = make_uint4(0, 0, 0, 0);
+    }
+    for (int i = tid; i < (kTileRows * 128) / 16; i += blockDim.x) {
+        reinterpret_cast<uint4*>(opH_hi)[i] = make_uint4(0, 0, 0, 0);
+        reinterpret_cast<uint4*>(opH_lo)[i] = make_uint4(0, 0, 0, 0);
+    }
 
     // ---- rays (ray_sampler.py:43-63)
     if (tid < R) {
@@ -217,6 +285,9 @@ __global__ void __launch_bounds__(kMaxThreads) render_kernel(const RenderK K) {
             float* r = sRay + tid * 8;
             r[0] = o[0]; r[1] = o[1]; r[2] = o[2];
             r[3] = wv[0] / nrm; r[4] = wv[1] / nrm; r[5] = wv[2] / nrm;
+        } else {
+            float* r = sRay + tid * 8;
+            r[0] = r[1] = r[2] = r[3] = r[4] = r[5] = 0.f;
         }
         // sample index -> image of this ray (tail rays of the last CTA reuse the last valid ray; their results are never stored)
         sRay[tid * 8 + 6] = __int_as_float((int)(min(gr, total_rays - 1) / K.M));
@@ -232,27 +303,127 @@ __global__ void __launch_bounds__(kMaxThreads) render_kernel(const RenderK K) {
         }
         sTc[s] = t;
     }
+    tc_fence_before();
     __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
 
     const float scale = 2.f / P.box_warp;
     const int64_t plane_img = (int64_t)3 * P.PH * P.PW * kFeat;
+    const uint64_t dhi64 = umma_desc_hi(32), dhi128 = umma_desc_hi(64);
+    uint32_t mma_phase = 0;
 
-    // ---- coarse pass: gather (warp per sample) then decode (thread per sample)
-    {
-        int r = warp / Dc, k = warp - r * Dc;                  // sample s = r * Dc + k, advanced without divisions
+    // gather + decode of `cnt` samples (depths in sT, R rays x D samples) into rows[cnt][33]
+    auto gather_decode = [&](const float* sT, int D, float* rows) {
+        const int cnt = R * D;
+        {
+            int r = warp / D, k = warp - r * D;                  // sample s = r * D + k, advanced without divisions
 #pragma unroll 2
-        for (int s = warp; s < R * Dc; s += nwarps) {
-            const float* ry = sRay + r * 8;
-            const float t = sTc[s];
-            sC[s * kRowStride + lane] = triplane_feature(P.planes + (int64_t)__float_as_int(ry[6]) * plane_img, P.PH, P.PW, ry[0] + t * ry[3],
-                                                         ry[1] + t * ry[4], ry[2] + t * ry[5], scale, lane);
-            k += nwarps;
-            while (k >= Dc) { k -= Dc; ++r; }
+            for (int s = warp; s < cnt; s += nwarps) {
+                const float* ry = sRay + r * 8;
+                const float t = sT[s];
+                const float feat = triplane_feature(P.planes + (int64_t)__float_as_int(ry[6]) * plane_img, P.PH, P.PW, ry[0] + t * ry[3],
+                                                    ry[1] + t * ry[4], ry[2] + t * ry[5], scale, lane);
+                __nv_bfloat16 h, l;
+                split_bf16(feat, h, l);
+                const uint32_t off = sw64_off(s, lane * 2);
+                *reinterpret_cast<__nv_bfloat16*>(opF_hi + off) = h;
+                *reinterpret_cast<__nv_bfloat16*>(opF_lo + off) = l;
+                k += nwarps;
+                while (k >= D) { k -= D; ++r; }
+            }
         }
-    }
-    __syncthreads();
-    for (int s = tid; s < R * Dc; s += blockDim.x) decode_row(sC + s * kRowStride, sW0, sB0, sW1t, sB1);
-    __syncthreads();
+        fence_proxy_async_smem();
+        __syncthreads();
+        // ---- layer 1 on the tensor cores
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t idesc = umma_idesc_bf16(kHidden);
+            const uint32_t a_hi = smem_u32(opF_hi), a_lo = smem_u32(opF_lo), b_hi = smem_u32(opW0_hi), b_lo = smem_u32(opW0_lo);
+#pragma unroll
+            for (int k16 = 0; k16 < kFeat / 16; ++k16) {
+                const uint32_t ko = (uint32_t)k16 * 32u;
+                umma_bf16(tmem, umma_desc(a_hi + ko, dhi64), umma_desc(b_hi + ko, dhi64), idesc, k16 != 0);
+                umma_bf16(tmem, umma_desc(a_hi + ko, dhi64), umma_desc(b_lo + ko, dhi64), idesc, 1u);
+                umma_bf16(tmem, umma_desc(a_lo + ko, dhi64), umma_desc(b_hi + ko, dhi64), idesc, 1u);
+            }
+            umma_commit(bar);
+        }
+        mbar_wait(bar, mma_phase, nullptr, 0);
+        mma_phase ^= 1u;
+        tc_fence_after();
+        // ---- epilogue 1: thread = row (TMEM lane); softplus(acc + b0) -> split -> layer-2 A tile
+        if (tid < kTileRows) {
+            const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+            for (int c16 = 0; c16 < kHidden; c16 += 16) {
+                uint32_t rr[16];
+                tmem_ld16(t_row + (uint32_t)c16, rr);
+                uint32_t ph[8], pl[8];
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                    __nv_bfloat16 h0, l0, h1, l1;
+                    split_bf16(softplus_fast(__uint_as_float(rr[j]) + sB0[c16 + j]), h0, l0);
+                    split_bf16(softplus_fast(__uint_as_float(rr[j + 1]) + sB0[c16 + j + 1]), h1, l1);
+                    ph[j >> 1] = pack_bf16x2(h0, h1);
+                    pl[j >> 1] = pack_bf16x2(l0, l1);
+                }
+                if (tid < cnt) {
+                    const uint32_t o0 = sw128_off(tid, c16 * 2), o1 = sw128_off(tid, c16 * 2 + 16);
+                    *reinterpret_cast<uint4*>(opH_hi + o0) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                    *reinterpret_cast<uint4*>(opH_hi + o1) = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+                    *reinterpret_cast<uint4*>(opH_lo + o0) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                    *reinterpret_cast<uint4*>(opH_lo + o1) = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+                }
+            }
+        }
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncthreads();
+        // ---- layer 2
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t idesc = umma_idesc_bf16(kN2);
+            const uint32_t a_hi = smem_u32(opH_hi), a_lo = smem_u32(opH_lo), b_hi = smem_u32(opW1_hi), b_lo = smem_u32(opW1_lo);
+            const uint32_t d = tmem + (uint32_t)kHidden;
+#pragma unroll
+            for (int k16 = 0; k16 < kHidden / 16; ++k16) {
+                const uint32_t ko = (uint32_t)k16 * 32u;
+                umma_bf16(d, umma_desc(a_hi + ko, dhi128), umma_desc(b_hi + ko, dhi128), idesc, k16 != 0);
+                umma_bf16(d, umma_desc(a_hi + ko, dhi128), umma_desc(b_lo + ko, dhi128), idesc, 1u);
+                umma_bf16(d, umma_desc(a_lo + ko, dhi128), umma_desc(b_hi + ko, dhi128), idesc, 1u);
+            }
+            umma_commit(bar);
+        }
+        mbar_wait(bar, mma_phase, nullptr, 0);
+        mma_phase ^= 1u;
+        tc_fence_after();
+        // ---- epilogue 2: sigma = o[0], rgb = sigmoid(o[1..32]) * 1.002 - 0.001 (triplane_next3d.py:369-370)
+        if (tid < kTileRows) {
+            const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)kHidden;
+            float* row = rows + tid * kRowStride;
+#pragma unroll
+            for (int c16 = 0; c16 < kN2; c16 += 16) {
+                uint32_t rr[16];
+                tmem_ld16(t_row + (uint32_t)c16, rr);
+                if (tid < cnt) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int o = c16 + j;
+                        if (o >= kOut) continue;
+                        const float val = __uint_as_float(rr[j]) + sB1[o];
+                        if (o == 0) row[32] = val;
+                        else row[o - 1] = sigmoid_fast(val) * 1.002f - 0.001f;
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+    };
+
+    // ---- coarse pass
+    gather_decode(sTc, Dc, sC);
 
     // ---- per ray (one warp each): coarse weights -> smoothed pdf -> inverse-CDF samples (renderer.py:209-268)
     for (int r = warp; r < R; r += nwarps) {
@@ -310,21 +481,7 @@ __global__ void __launch_bounds__(kMaxThreads) render_kernel(const RenderK K) {
     __syncthreads();
 
     // ---- fine pass
-    {
-        int r = warp / Df, k = warp - r * Df;
-#pragma unroll 2
-        for (int s = warp; s < R * Df; s += nwarps) {
-            const float* ry = sRay + r * 8;
-            const float t = sTf[s];
-            sF[s * kRowStride + lane] = triplane_feature(P.planes + (int64_t)__float_as_int(ry[6]) * plane_img, P.PH, P.PW, ry[0] + t * ry[3],
-                                                         ry[1] + t * ry[4], ry[2] + t * ry[5], scale, lane);
-            k += nwarps;
-            while (k >= Df) { k -= Df; ++r; }
-        }
-    }
-    __syncthreads();
-    for (int s = tid; s < R * Df; s += blockDim.x) decode_row(sF + s * kRowStride, sW0, sB0, sW1t, sB1);
-    __syncthreads();
+    gather_decode(sTf, Df, sF);
 
     // ---- per ray (one warp each): stable sort-merge of coarse (already sorted) and fine depths by rank counting
     //      (torch.sort on the concatenation, renderer.py:164-182: ties keep coarse before fine and fine in input order),
@@ -396,6 +553,10 @@ __global__ void __launch_bounds__(kMaxThreads) render_kernel(const RenderK K) {
         if (dmin < INFINITY) atomicMin(reinterpret_cast<int*>(P.depth_minmax), __float_as_int(dmin));
         if (dmax > -INFINITY) atomicMax(reinterpret_cast<int*>(P.depth_minmax) + 1, __float_as_int(dmax));
     }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u) : "memory");
+    }
 }
 
 __global__ void __launch_bounds__(256) depth_clamp_kernel(float* __restrict__ depth, int64_t n, const float* __restrict__ mm) {
@@ -448,9 +609,10 @@ __global__ void __launch_bounds__(kMaxThreads) sample_points_kernel(const float*
 
 size_t render_smem_bytes(int R, int Dc, int Df) {
     const int Dt = Dc + Df;
-    size_t fl = (size_t)kHidden * kFeat + kHidden * kW1Stride + kHidden + kW1Stride + (size_t)R * Dc * kRowStride + (size_t)R * Df * kRowStride +
-                (size_t)R * Dc + (size_t)R * Df + (size_t)R * Dt * 4 + (size_t)R * 8;
-    return fl * sizeof(float) + (size_t)R * Dt + 16;
+    const size_t operands = (size_t)2 * kTileRows * 64 + 2 * kTileRows * 128 + 2 * kHidden * 64 + 2 * kN2 * 128;      // F, H, W0, W1 (hi + lo)
+    const size_t fl = (size_t)kHidden + kN2 + (size_t)R * Dc * kRowStride + (size_t)R * Df * kRowStride + (size_t)R * Dc + (size_t)R * Df +
+                      (size_t)R * Dt * 4 + (size_t)R * 8;
+    return 1024 + operands + fl * sizeof(float) + (size_t)R * Dt + 16;
 }
 }  // namespace
 
@@ -466,24 +628,18 @@ extern "C" int n3d_render_rays(const N3DRender* p, void* stream) {
     K.p = *p;
     K.M = p->res * p->res;
     const int dmax = p->depth_coarse > p->depth_fine ? p->depth_coarse : p->depth_fine;
-    static int target_threads = 0;
-    if (!target_threads) {
-        const char* e = getenv("N3D_RENDER_THREADS");          // tuning knob: threads (= rays x samples) per CTA
-        target_threads = e ? atoi(e) : kMaxThreads;
-        if (target_threads < 32 || target_threads > kMaxThreads) target_threads = kMaxThreads;
-    }
-    K.rays_per_cta = target_threads / dmax;
+    K.rays_per_cta = kTileRows / dmax;                          // all samples of a pass form one 128-row UMMA tile
     if (K.rays_per_cta < 1) K.rays_per_cta = 1;
     K.delta_coarse = (float)(((double)p->ray_end - (double)p->ray_start) / (double)(p->depth_coarse - 1));
-    const int threads = ((K.rays_per_cta * dmax + 31) / 32) * 32;
+    const int threads = kRThreads;
     const size_t smem = render_smem_bytes(K.rays_per_cta, p->depth_coarse, p->depth_fine);
-    static size_t configured = 0;
-    if (smem > configured) {
+    static bool configured = false;
+    if (!configured) {
         if (cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
             n3d_set_error("n3d_render_rays: cannot raise dynamic shared memory");
             return N3D_ERR_CUDA;
         }
-        configured = 200 * 1024;
+        configured = true;
     }
     const int64_t total_rays = (int64_t)p->N * K.M;
     const int grid = (int)((total_rays + K.rays_per_cta - 1) / K.rays_per_cta);
