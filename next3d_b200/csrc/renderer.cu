@@ -222,8 +222,8 @@ __global__ void __launch_bounds__(kRThreads, 2) render_kernel(const RenderK K) {
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const uint64_t seed = P.seed_ptr ? (P.seed + __ldg(reinterpret_cast<const unsigned long long*>(P.seed_ptr))) : P.seed;
-    const int64_t ray0 = (int64_t)blockIdx.x * R;        // global ray index = n*M + m
     const int64_t total_rays = (int64_t)P.N * K.M;
+    const int64_t ngroups = (total_rays + R - 1) / R;
     const uint32_t bar = smem_u32(&s_bar);
 
     // ---- one-time setup: mbarrier, TMEM (128 columns), decoder weights -> bf16 (hi, lo) B-operand tiles
@@ -261,6 +261,19 @@ __global__ void __launch_bounds__(kRThreads, 2) render_kernel(const RenderK K) {
         reinterpret_cast<uint4*>(opH_lo)[i] = make_uint4(0, 0, 0, 0);
     }
 
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    const float scale = 2.f / P.box_warp;
+    const int64_t plane_img = (int64_t)3 * P.PH * P.PW * kFeat;
+    const uint64_t dhi64 = umma_desc_hi(32), dhi128 = umma_desc_hi(64);
+    uint32_t mma_phase = 0;
+    float dmin = INFINITY, dmax = -INFINITY;
+
+    // persistent CTA: decoder operands, TMEM and the mbarrier are set up once, then ray groups are processed in a loop
+    for (int64_t group = blockIdx.x; group < ngroups; group += gridDim.x) {
+    const int64_t ray0 = group * R;                       // global ray index = n*M + m
     // ---- rays (ray_sampler.py:43-63)
     if (tid < R) {
         const int64_t gr = ray0 + tid;
@@ -303,15 +316,7 @@ __global__ void __launch_bounds__(kRThreads, 2) render_kernel(const RenderK K) {
         }
         sTc[s] = t;
     }
-    tc_fence_before();
     __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = s_tmem;
-
-    const float scale = 2.f / P.box_warp;
-    const int64_t plane_img = (int64_t)3 * P.PH * P.PW * kFeat;
-    const uint64_t dhi64 = umma_desc_hi(32), dhi128 = umma_desc_hi(64);
-    uint32_t mma_phase = 0;
 
     // gather + decode of `cnt` samples (depths in sT, R rays x D samples) into rows[cnt][33]
     auto gather_decode = [&](const float* sT, int D, float* rows) {
@@ -486,7 +491,6 @@ __global__ void __launch_bounds__(kRThreads, 2) render_kernel(const RenderK K) {
     // ---- per ray (one warp each): stable sort-merge of coarse (already sorted) and fine depths by rank counting
     //      (torch.sort on the concatenation, renderer.py:164-182: ties keep coarse before fine and fine in input order),
     //      final weights, composite depth and colours (ray_marcher.py:27-66)
-    float dmin = INFINITY, dmax = -INFINITY;
     for (int r = warp; r < R; r += nwarps) {
         const int64_t gr = ray0 + r;
         if (gr >= total_rays) continue;
@@ -538,6 +542,8 @@ __global__ void __launch_bounds__(kRThreads, 2) render_kernel(const RenderK K) {
         P.rgb[gr * kFeat + lane] = acc * 2.f - 1.f;
     }
     __syncthreads();
+
+    }   // ray-group loop
 
     // ---- batch-global depth range (ray_marcher.py:54): warp + block reduce, then one atomic pair per CTA
 #pragma unroll
@@ -642,7 +648,15 @@ extern "C" int n3d_render_rays(const N3DRender* p, void* stream) {
         configured = true;
     }
     const int64_t total_rays = (int64_t)p->N * K.M;
-    const int grid = (int)((total_rays + K.rays_per_cta - 1) / K.rays_per_cta);
+    const int64_t ngroups = (total_rays + K.rays_per_cta - 1) / K.rays_per_cta;
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (num_sms <= 0) num_sms = 148;
+    }
+    const int grid = (int)(ngroups < 2 * num_sms ? ngroups : 2 * num_sms);       // persistent: 2 CTAs per SM loop over the ray groups
     render_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(K);
     N3D_CHECK_LAUNCH("n3d_render_rays");
     return N3D_OK;
