@@ -28,6 +28,18 @@ METRIC = 'generator images/sec at 512^2 (64^2 neural render, 48+48 samples/ray)'
 UNIT = 'img/s'
 
 
+def _traffic(kernel):
+    """Measured DRAM bytes per launch of `kernel` (dram__bytes_read + dram__bytes_write, ncu capture of one forward at the bench
+    batch size, summarised by tools/dram_table.py into profiles/): (bytes, source) or (None, None)."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r01_dram_traffic.json')
+    try:
+        with open(path) as f:
+            k = json.load(f)['kernels'][kernel]
+        return k['dram_bytes_per_launch'], 'profiles/r01_dram_traffic.json (ncu, %d launches of one batch-8 forward)' % k['launches']
+    except (OSError, KeyError, ValueError):
+        return None, None
+
+
 def _peaks():
     try:
         with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
@@ -239,8 +251,11 @@ def run_ours(args):
             pk = _peaks()
             n_g, ms_g, fl_g = summ['conv_gemm']
             ach = fl_g / (ms_g * 1e-3) / 1e12
+            tr_g, tr_src = _traffic('conv_gemm_kernel') if B == 8 else (None, None)
+            tr_r, _ = _traffic('render_kernel') if B == 8 else (None, None)
             roof = {'kernel': 'conv_gemm_kernel (tcgen05 implicit GEMM, all conv layers)', 'bound': 'tensor', 'achieved': ach, 'peak': pk['tf'],
-                    'unit': 'TFLOP/s', 'frac': ach / pk['tf'], 'traffic': None, 'peak_source': pk['src'], 'launches_per_step': n_g,
+                    'unit': 'TFLOP/s', 'frac': ach / pk['tf'], 'traffic': tr_g, 'traffic_unit': 'DRAM bytes per launch (mean)', 'traffic_source': tr_src,
+                    'peak_source': pk['src'], 'launches_per_step': n_g,
                     'ms_per_step': ms_g, 'share_of_step': ms_g / (1e3 * dt / args.steps),
                     'note': 'algorithmic FLOPs (one product per MAC: %.1f GFLOP/img); the bf16x3 scheme executes 3x that on the tensor pipe' % (fl_g / B / 1e9)}
             n_r, ms_r, _ = summ['render_rays']
@@ -248,7 +263,7 @@ def run_ours(args):
             bytes_img = 3 * 32 * 256 * 256 * 4 + M * 6 * 4 + M * 34 * 4            # planes once + rays + rgb32/depth/wsum out (RNG in kernel)
             ach_r = bytes_img * B / (ms_r * 1e-3) / 1e9
             roof_r = {'kernel': 'render_kernel (fused ray sampler + tri-plane fetch + MLP + compositing)', 'bound': 'hbm', 'achieved': ach_r,
-                      'peak': pk['hbm'], 'unit': 'GB/s', 'frac': ach_r / pk['hbm'], 'traffic': None, 'ms_per_step': ms_r,
+                      'peak': pk['hbm'], 'unit': 'GB/s', 'frac': ach_r / pk['hbm'], 'traffic': tr_r, 'algorithmic_bytes_per_launch': bytes_img * B, 'ms_per_step': ms_r,
                       'share_of_step': ms_r / (1e3 * dt / args.steps), 'flops_per_image': M * D_ * 8320}
     if rank != 0:
         if world > 1:

@@ -98,6 +98,18 @@ typedef struct {
     int32_t coff;         /* channel offset in the destination */
 } N3DSplitOut;
 
+/* Optional ToRGB layer (networks_stylegan2.py:353-357) fused into the epilogue of the convolution that produces its input,
+ * for image widths <= 4 (the super-resolution blocks): rgb[n,c,pixel] (+)= clamp(sum_o v[n,pixel,o] * style[n,o] * weight[c,o] + bias[c]).
+ * Requires all Cout channels of a pixel in one tile (Cout <= 256) and TN == 1 tiles (resolution >= 16). out == NULL disables it. */
+typedef struct {
+    float* out;            /* fp32 image, NHWC [N,OH,OW,channels] or NCHW */
+    const float* weight;   /* [channels, Cout] fp32 */
+    const float* style;    /* [N, Cout] fp32 (ToRGB affine output, already multiplied by 1/sqrt(Cout)) */
+    const float* bias;     /* [channels] */
+    float clamp;           /* < 0 = none */
+    int32_t channels, nchw, accumulate;
+} N3DFusedRgb;
+
 /* One implicit-GEMM convolution on tcgen05 tensor cores (bf16 hi/lo operands, 3 products, fp32 accumulate in TMEM):
  *   acc[n, y, x, o] = sum_taps sum_i A[n + tap.img_off*a_img_mul, y + tap.dy, x + tap.dx, i] * Wp[tap.wtap, o, i]
  * over an M-space of N x MH x MW "tile pixels"; out-of-range A reads are zero (this is the conv padding).
@@ -123,6 +135,7 @@ typedef struct {
     N3DSplitOut out[2];
     float* out_f32; int32_t f32_cstride, f32_coff, f32_nchw, f32_accumulate;
     int32_t oy_mul, oy_off, ox_mul, ox_off, OH, OW;
+    N3DFusedRgb rgb;
 } N3DConvGemm;
 
 int n3d_conv_gemm(const N3DConvGemm* p, void* stream);

@@ -30,6 +30,10 @@ class SplitOut(C.Structure):
     _fields_ = [('hi', P), ('lo', P), ('style', P), ('cstride', I32), ('coff', I32)]
 
 
+class FusedRgb(C.Structure):
+    _fields_ = [('out', P), ('weight', P), ('style', P), ('bias', P), ('clamp', F32), ('channels', I32), ('nchw', I32), ('accumulate', I32)]
+
+
 class ConvGemm(C.Structure):
     _fields_ = [
         ('a_hi', P), ('a_lo', P), ('NI', I32), ('AH', I32), ('AW', I32), ('Cin', I32),
@@ -42,6 +46,7 @@ class ConvGemm(C.Structure):
         ('out', SplitOut * 2),
         ('out_f32', P), ('f32_cstride', I32), ('f32_coff', I32), ('f32_nchw', I32), ('f32_accumulate', I32),
         ('oy_mul', I32), ('oy_off', I32), ('ox_mul', I32), ('ox_off', I32), ('OH', I32), ('OW', I32),
+        ('rgb', FusedRgb),
     ]
 
 

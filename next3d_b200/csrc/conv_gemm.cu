@@ -26,6 +26,7 @@ constexpr int kBlockM = 128;
 // 32 bf16 (64-byte rows, SWIZZLE_64B) so that no TMA box hangs over the channel extent.
 constexpr int kThreads = 384;                 // warps 0-3: producer / MMA / TMEM alloc / spare; 4-7 and 8-11: two epilogue groups
 constexpr int kMaxBlockN = 256;
+constexpr int kStageArrays = 8;               // dcoef | bias | style0 | style1 | up to 4 modulated ToRGB weight rows
 
 struct KParams {
     CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
@@ -43,11 +44,17 @@ struct KParams {
     float gain, slope, clamp;
     N3DSplitOut out[2];
     float* out_f32; int f32_cstride, f32_coff, f32_nchw, f32_accumulate;
+    N3DFusedRgb rgb;                 // optional fused ToRGB (<= 4 image channels), see include/next3d_b200.h
     int oy_mul, ox_mul, OH, OW;
     int* err_flag;
 };
 
+__device__ __forceinline__ int staged_rgb_channels(const KParams& P) { return (P.rgb.out && P.TN == 1 && P.mode == 0 && P.tiles_n == 1) ? P.rgb.channels : 0; }
+
 struct TileInfo { int sub, tn, x0, y0, n0; };
+// Tiles are numbered sub-problem-major (all tiles of parity class 0, then class 1, ...), n-tile minor.  Interleaving the classes
+// of one spatial tile across neighbouring CTAs (better L2 re-use of the shared activation tile) was measured 0-35 % slower on
+// B200: the kernel is bound by L2->SM fill bandwidth, not DRAM, and the interleaved schedule balances the 4/2/2/1-tap classes worse.
 __device__ __forceinline__ TileInfo decode_tile(const KParams& P, int tile) {
     int sidx = 0, begin = 0;
     while (sidx + 1 < P.nsub && tile >= P.sub[sidx].tile_end) { begin = P.sub[sidx].tile_end; ++sidx; }
@@ -135,9 +142,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.block_n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
             const uint64_t dhi = umma_desc_hi(P.block_k);
             const int k16 = P.block_k / 16;
-            int s = 0; uint32_t ph = 0; int acc = 0; uint32_t acc_ph = 0;
+            int s = 0; uint32_t ph = 0; int cnt = 0;            // cnt: tiles of this CTA so far -> accumulator buffer (parity) + barrier phase
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int ksteps = P.sub[decode_tile(P, tile).sub].ntaps * P.cin_chunks;
+                const int sub = decode_tile(P, tile).sub;
+                const int ksteps = P.sub[sub].ntaps * P.cin_chunks;
+                const int acc = cnt & 1;
+                const uint32_t acc_ph = (uint32_t)(cnt >> 1) & 1u;
+                ++cnt;
                 mbar_wait(tempty_bar(acc), acc_ph ^ 1u, P.err_flag, 2);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P.acc_stride);
@@ -158,7 +169,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                     if (++s == P.stages) { s = 0; ph ^= 1u; }
                 }
                 umma_commit(tfull_bar(acc));                   // accumulator complete -> epilogue
-                if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
             }
         }
     } else if (warp >= 4) {
@@ -169,11 +179,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         const int gtid = (warp - 4 - 4 * g) * 32 + lane;       // thread index inside the group (0..127)
         const int tw = row % P.TW, th = (row / P.TW) % P.TH, tnn = row / (P.TW * P.TH);
         // per-group staging of the per-channel epilogue vectors of the current tile: [dcoef | bias | style0 | style1][block_n]
-        float* stg = reinterpret_cast<float*>(smem_raw + (stage_area_off + (uint32_t)g * 4u * (uint32_t)kMaxBlockN * 4u));
+        float* stg = reinterpret_cast<float*>(smem_raw + (stage_area_off + (uint32_t)g * (uint32_t)kStageArrays * (uint32_t)kMaxBlockN * 4u));
+        const int nrgb = staged_rgb_channels(P);
         const bool staged = (P.TN == 1) && (P.mode == 0);
-        uint32_t acc_ph = 0;
-        for (int tile = blockIdx.x + g * gridDim.x; tile < total_tiles; tile += 2 * gridDim.x) {
+        int cnt = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const TileInfo ti = decode_tile(P, tile);
+            const bool mine = (cnt & 1) == g;                  // this CTA's tiles alternate between the two accumulators / groups
+            const uint32_t acc_ph = (uint32_t)(cnt >> 1) & 1u;
+            ++cnt;
+            if (!mine) continue;
             const int tn = ti.tn, n0 = ti.n0;
             const int x = ti.x0 + tw, y = ti.y0 + th;
             const int n = n0 + tnn;
@@ -194,12 +209,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                     }
                     stg[arr * kMaxBlockN + c] = val;
                 }
+                for (int i = gtid; i < nrgb * P.block_n; i += 128) {          // fused ToRGB: W_rgb[c, co] * style_rgb[n, co]
+                    const int c = i / P.block_n, co = i - c * P.block_n;
+                    float val = 0.f;
+                    if (co < P.Cout && n0 < P.N) val = __ldg(P.rgb.weight + (int64_t)c * P.Cout + co) * __ldg(P.rgb.style + (int64_t)n0 * P.Cout + co);
+                    stg[(4 + c) * kMaxBlockN + co] = val;
+                }
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
             }
 
             mbar_wait(tfull_bar(g), acc_ph, P.err_flag, 4);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * P.acc_stride);
+            float racc[4] = {0.f, 0.f, 0.f, 0.f};
             for (int c16 = 0; c16 < P.block_n; c16 += 16) {
                 uint32_t r[16];
                 __syncwarp();                                  // tcgen05.ld is warp-collective (.sync.aligned)
@@ -225,6 +247,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                             a = (a > 0.f ? a : a * P.slope) * P.gain;
                             if (P.clamp >= 0.f) a = fminf(fmaxf(a, -P.clamp), P.clamp);
                             v[j] = a; s0[j] = pv[e]; s1[j] = qv[e];
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        if (c < nrgb) {
+                            const float4* w4 = reinterpret_cast<const float4*>(stg + (4 + c) * kMaxBlockN + c16);
+#pragma unroll
+                            for (int j4 = 0; j4 < 4; ++j4) {
+                                const float4 w = w4[j4];
+                                racc[c] = fmaf(v[j4 * 4], w.x, racc[c]); racc[c] = fmaf(v[j4 * 4 + 1], w.y, racc[c]);
+                                racc[c] = fmaf(v[j4 * 4 + 2], w.z, racc[c]); racc[c] = fmaf(v[j4 * 4 + 3], w.w, racc[c]);
+                            }
                         }
                     }
                 } else {
@@ -289,29 +323,42 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 for (int k = 0; k < 2; ++k) {
                     const N3DSplitOut o = P.out[k];
                     if (!o.hi) continue;
-                    __nv_bfloat16 h[16], l[16];
+                    uint32_t h[8], l[8];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) split_bf16(v[j] * (k == 0 ? s0[j] : s1[j]), h[j], l[j]);
+                    for (int j = 0; j < 8; ++j)
+                        split_bf16x2(v[2 * j] * (k == 0 ? s0[2 * j] : s1[2 * j]), v[2 * j + 1] * (k == 0 ? s0[2 * j + 1] : s1[2 * j + 1]), h[j], l[j]);
                     __nv_bfloat16* dh = (__nv_bfloat16*)o.hi + opix * o.cstride + o.coff + co0;
                     __nv_bfloat16* dl = (__nv_bfloat16*)o.lo + opix * o.cstride + o.coff + co0;
                     if (nco == 16 && (((o.cstride | (o.coff + co0)) & 7) == 0)) {
 #pragma unroll
-                        for (int j = 0; j < 16; j += 8) {
-                            *reinterpret_cast<uint4*>(dh + j) = make_uint4(pack_bf16x2(h[j], h[j + 1]), pack_bf16x2(h[j + 2], h[j + 3]),
-                                                                           pack_bf16x2(h[j + 4], h[j + 5]), pack_bf16x2(h[j + 6], h[j + 7]));
-                            *reinterpret_cast<uint4*>(dl + j) = make_uint4(pack_bf16x2(l[j], l[j + 1]), pack_bf16x2(l[j + 2], l[j + 3]),
-                                                                           pack_bf16x2(l[j + 4], l[j + 5]), pack_bf16x2(l[j + 6], l[j + 7]));
+                        for (int j = 0; j < 8; j += 4) {
+                            *reinterpret_cast<uint4*>(dh + 2 * j) = make_uint4(h[j], h[j + 1], h[j + 2], h[j + 3]);
+                            *reinterpret_cast<uint4*>(dl + 2 * j) = make_uint4(l[j], l[j + 1], l[j + 2], l[j + 3]);
                         }
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) if (j < nco) { dh[j] = h[j]; dl[j] = l[j]; }
+                        for (int j = 0; j < 16; ++j)
+                            if (j < nco) {
+                                dh[j] = __ushort_as_bfloat16((unsigned short)(h[j >> 1] >> ((j & 1) * 16)));
+                                dl[j] = __ushort_as_bfloat16((unsigned short)(l[j >> 1] >> ((j & 1) * 16)));
+                            }
+                    }
+                }
+            }
+            if (nrgb > 0 && valid) {                       // ToRGBLayer: linear bias (+ clamp), added to the up-sampled skip image
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (c < nrgb) {
+                        float o = racc[c] + __ldg(P.rgb.bias + c);
+                        if (P.rgb.clamp >= 0.f) o = fminf(fmaxf(o, -P.rgb.clamp), P.rgb.clamp);
+                        float* dst = P.rgb.nchw ? P.rgb.out + (((int64_t)n * nrgb + c) * P.OH + oy) * P.OW + ox : P.rgb.out + opix * nrgb + c;
+                        *dst = P.rgb.accumulate ? (*dst + o) : o;
                     }
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(g));
-            acc_ph ^= 1u;
         }
     }
 
@@ -411,6 +458,12 @@ int launch_conv(const N3DConvGemm* p, int nsub, const SubSpec* specs, void* stre
             break;
         }
         while (bn > 32 && tiles_m * n3d_div_up(p->Cout, bn) < 148) bn = (bn == 96) ? 32 : bn / 2;
+        if (p->rgb.out) {                                   // fused ToRGB needs every output channel of a pixel in one tile
+            N3D_CHECK_ARG(cout16 <= 256 && cout16 % 16 == 0, "n3d_conv_gemm: fused ToRGB needs Cout <= 256");
+            N3D_CHECK_ARG(p->rgb.channels >= 1 && p->rgb.channels <= 4 && p->rgb.weight && p->rgb.style && p->rgb.bias, "n3d_conv_gemm: bad fused ToRGB descriptor");
+            N3D_CHECK_ARG(p->mode == 0 && nsub == 1 && K.TN == 1, "n3d_conv_gemm: fused ToRGB needs mode 0 and >= 128 output positions per image");
+            bn = cout16;
+        }
     }
     K.block_n = bn;
     K.tiles_n = n3d_div_up(p->Cout, bn);
@@ -420,7 +473,7 @@ int launch_conv(const N3DConvGemm* p, int nsub, const SubSpec* specs, void* stre
     K.a_bytes = kBlockM * K.block_k * 2;
     K.b_bytes = bn * K.block_k * 2;
     K.stage_bytes = 2 * K.a_bytes + 2 * K.b_bytes;
-    K.stages = min(6, (200 * 1024) / K.stage_bytes);      // + 8 KiB epilogue staging + barriers + 1 KiB alignment slack <= 227 KiB
+    K.stages = min(6, (200 * 1024) / K.stage_bytes);      // + 16 KiB epilogue staging + barriers + 1 KiB alignment slack <= 227 KiB
     K.cin_chunks = n3d_div_up(p->Cin, K.block_k);
     K.ntaps = tap_total; K.nprod = p->nprod; K.a_img_stride = p->a_img_mul;
     {
@@ -432,6 +485,7 @@ int launch_conv(const N3DConvGemm* p, int nsub, const SubSpec* specs, void* stre
     K.out[0] = p->out[0]; K.out[1] = p->out[1];
     K.out_f32 = p->out_f32; K.f32_cstride = p->f32_cstride; K.f32_coff = p->f32_coff; K.f32_nchw = p->f32_nchw;
     K.f32_accumulate = p->f32_accumulate;
+    K.rgb = p->rgb;
     K.oy_mul = p->oy_mul; K.ox_mul = p->ox_mul; K.OH = p->OH; K.OW = p->OW;
     if (!g_err_flag) {
         if (cudaMalloc(&g_err_flag, sizeof(int)) != cudaSuccess) { n3d_set_error("n3d_conv_gemm: cudaMalloc(err flag) failed"); return N3D_ERR_CUDA; }
@@ -451,7 +505,7 @@ int launch_conv(const N3DConvGemm* p, int nsub, const SubSpec* specs, void* stre
         if ((rc = make_tmap(&K.tmB_lo, p->w_lo, 3, wdims, wbox, K.block_k)) != N3D_OK) return rc;
     }
 
-    const int smem = K.stages * K.stage_bytes + 8 * (2 * K.stages + 4) + 32 + 2 * 4 * kMaxBlockN * 4 + 1024;
+    const int smem = K.stages * K.stage_bytes + 8 * (2 * K.stages + 4) + 32 + 2 * kStageArrays * kMaxBlockN * 4 + 1024;
     static int smem_configured = 0;
     if (smem > smem_configured) {
         if (cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {

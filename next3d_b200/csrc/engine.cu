@@ -83,11 +83,11 @@ __global__ void __launch_bounds__(256) modulate_split_kernel(const float* __rest
             const float4 s = __ldg(reinterpret_cast<const float4*>(style + (int64_t)n * C) + c4);
             v.x *= s.x; v.y *= s.y; v.z *= s.z; v.w *= s.w;
         }
-        __nv_bfloat16 h[4], l[4];
-        split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]); split_bf16(v.z, h[2], l[2]); split_bf16(v.w, h[3], l[3]);
+        uint2 h, l;
+        split_bf16x2(v.x, v.y, h.x, l.x); split_bf16x2(v.z, v.w, h.y, l.y);
         const int64_t o = pix * cstride + coff + c4 * 4;
-        *reinterpret_cast<uint2*>(hi + o) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
-        *reinterpret_cast<uint2*>(lo + o) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+        *reinterpret_cast<uint2*>(hi + o) = h;
+        *reinterpret_cast<uint2*>(lo + o) = l;
     }
 }
 
@@ -102,136 +102,208 @@ struct EpiParams {
     float* out_f32; int f32_cstride, f32_coff;
 };
 
-__device__ __forceinline__ float4 f4_fma(float w, const float4& v, const float4& a) { return make_float4(fmaf(w, v.x, a.x), fmaf(w, v.y, a.y), fmaf(w, v.z, a.z), fmaf(w, v.w, a.w)); }
-__device__ __forceinline__ float4 f4_scale(float w, const float4& v) { return make_float4(w * v.x, w * v.y, w * v.z, w * v.w); }
+// float4 arithmetic on the packed fp32x2 pipe (FFMA2 / FMUL2 / FADD2, sm_100): half the issue slots of scalar code.
+__device__ __forceinline__ float2 f4lo(const float4& v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 f4hi(const float4& v) { return make_float2(v.z, v.w); }
+__device__ __forceinline__ float4 f4_join(const float2& a, const float2& b) { return make_float4(a.x, a.y, b.x, b.y); }
+__device__ __forceinline__ float4 f4_fma(float w, const float4& v, const float4& a) {
+    const float2 ww = make_float2(w, w);
+    return f4_join(__ffma2_rn(ww, f4lo(v), f4lo(a)), __ffma2_rn(ww, f4hi(v), f4hi(a)));
+}
+__device__ __forceinline__ float4 f4_fma4(const float4& w, const float4& v, const float4& a) {
+    return f4_join(__ffma2_rn(f4lo(w), f4lo(v), f4lo(a)), __ffma2_rn(f4hi(w), f4hi(v), f4hi(a)));
+}
+__device__ __forceinline__ float4 f4_mul4(const float4& w, const float4& v) { return f4_join(__fmul2_rn(f4lo(w), f4lo(v)), __fmul2_rn(f4hi(w), f4hi(v))); }
+__device__ __forceinline__ float4 f4_scale(float w, const float4& v) {
+    const float2 ww = make_float2(w, w);
+    return f4_join(__fmul2_rn(ww, f4lo(v)), __fmul2_rn(ww, f4hi(v)));
+}
 
-__device__ __forceinline__ void epi_store(const EpiParams& E, float4 acc, int n, int y, int x, int H2, int W2, int C, int c0) {
-    float v[4] = {acc.x, acc.y, acc.z, acc.w};
-    const float nz = E.noise ? __ldg(E.noise + (int64_t)n * E.noise_nstride + (int64_t)y * W2 + x) : 0.f;
+// Per-thread epilogue constants of one (image, 4-channel group): demodulation and bias pre-multiplied by the activation gain
+// (lrelu(a) * g == lrelu(a * g) for g > 0), the two consumers' styles.
+struct EpiVec { float4 dcg, bsg, st[2]; };
+
+__device__ __forceinline__ EpiVec epi_load(const EpiParams& E, int n, int C, int c0) {
+    EpiVec V;
     float4 dc = make_float4(1.f, 1.f, 1.f, 1.f), bs = make_float4(0.f, 0.f, 0.f, 0.f);
     if (E.dcoef) dc = __ldg(reinterpret_cast<const float4*>(E.dcoef + (int64_t)n * C + c0));
     if (E.bias) bs = __ldg(reinterpret_cast<const float4*>(E.bias + c0));
-    const float dcv[4] = {dc.x, dc.y, dc.z, dc.w}, bsv[4] = {bs.x, bs.y, bs.z, bs.w};
+    V.dcg = f4_scale(E.gain, dc); V.bsg = f4_scale(E.gain, bs);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        float a = v[j] * dcv[j] + nz + bsv[j];
-        a = (a > 0.f ? a : a * E.slope) * E.gain;
-        if (E.clamp >= 0.f) a = fminf(fmaxf(a, -E.clamp), E.clamp);
-        v[j] = a;
+    for (int k = 0; k < 2; ++k) {
+        V.st[k] = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (E.out[k].hi && E.out[k].style) V.st[k] = __ldg(reinterpret_cast<const float4*>(E.out[k].style + (int64_t)n * C + c0));
     }
-    const int64_t pix = ((int64_t)n * H2 + y) * W2 + x;
-    if (E.out_f32) *reinterpret_cast<float4*>(E.out_f32 + pix * E.f32_cstride + E.f32_coff + c0) = make_float4(v[0], v[1], v[2], v[3]);
+    return V;
+}
+
+// Output cursors of one thread: element offsets of its current 2x2 block's top-left pixel in the fp32 output and in the two split
+// outputs (channel offset included), advanced by two rows per strip step -- no 64-bit multiplies in the loop.
+struct EpiCursor { int64_t f32, sp[2]; };
+
+__device__ __forceinline__ EpiCursor epi_cursor(const EpiParams& E, int64_t pix, int c0) {
+    EpiCursor P;
+    P.f32 = pix * E.f32_cstride + E.f32_coff + c0;
+    P.sp[0] = pix * E.out[0].cstride + E.out[0].coff + c0;
+    P.sp[1] = pix * E.out[1].cstride + E.out[1].coff + c0;
+    return P;
+}
+
+// bias_act (lrelu with 0 <= slope <= 1: max(t, slope * t)) + clamp + the fp32 / modulated split-bf16 stores of one pixel.
+// nzg = noise * gain; dpix = pixel offset from the cursor (0, 1, W2, W2 + 1).
+__device__ __forceinline__ void epi_store(const EpiParams& E, const EpiVec& V, const EpiCursor& P, const float4& acc, float nzg, int dpix) {
+    float4 t = f4_fma4(acc, V.dcg, make_float4(V.bsg.x + nzg, V.bsg.y + nzg, V.bsg.z + nzg, V.bsg.w + nzg));
+    const float4 ts = f4_scale(E.slope, t);
+    t = make_float4(fmaxf(t.x, ts.x), fmaxf(t.y, ts.y), fmaxf(t.z, ts.z), fmaxf(t.w, ts.w));
+    if (E.clamp >= 0.f) {
+        const float c = E.clamp;
+        t = make_float4(fminf(fmaxf(t.x, -c), c), fminf(fmaxf(t.y, -c), c), fminf(fmaxf(t.z, -c), c), fminf(fmaxf(t.w, -c), c));
+    }
+    if (E.out_f32) *reinterpret_cast<float4*>(E.out_f32 + P.f32 + dpix * E.f32_cstride) = t;
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
         const N3DSplitOut o = E.out[k];
         if (!o.hi) continue;
-        float4 st = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (o.style) st = __ldg(reinterpret_cast<const float4*>(o.style + (int64_t)n * C + c0));
-        const float sv[4] = {st.x, st.y, st.z, st.w};
-        __nv_bfloat16 h[4], l[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) split_bf16(v[j] * sv[j], h[j], l[j]);
-        const int64_t off = pix * o.cstride + o.coff + c0;
-        *reinterpret_cast<uint2*>((__nv_bfloat16*)o.hi + off) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
-        *reinterpret_cast<uint2*>((__nv_bfloat16*)o.lo + off) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+        const float4 m = f4_mul4(t, V.st[k]);
+        uint2 h, l;
+        split_bf16x2(m.x, m.y, h.x, l.x); split_bf16x2(m.z, m.w, h.y, l.y);
+        const int64_t off = P.sp[k] + dpix * o.cstride;
+        *reinterpret_cast<uint2*>((__nv_bfloat16*)o.hi + off) = h;
+        *reinterpret_cast<uint2*>((__nv_bfloat16*)o.lo + off) = l;
     }
 }
 
-// thread = (2x2 block of output pixels, 4-channel group).  The 4x4 FIR is separable ([1,3,3,1]/8 * 2 per axis): five raw rows
-// of five float4 each are streamed through registers, each row contributing to the two output rows -> 25 loads per 4 outputs
-// instead of 64 (the straightforward form is L1-bandwidth bound).
-__global__ void __launch_bounds__(256) fir_up_epilogue_kernel(const float* __restrict__ raw, int N, int H2, int W2, int C, EpiParams E) {
-    const int RH = H2 + 1, RW = W2 + 1, c4n = C >> 2, BH = H2 >> 1, BW = W2 >> 1;
-    const int64_t total = (int64_t)N * BH * BW * c4n;
+// Horizontal pass of the separable 4-tap FIR for one raw row: the two outputs that start at columns xs and xs+1 (5 float4 loads
+// at p, p + cs, ..., p + 4 cs; only the first / last column can fall outside the image: flags vl / vr).  `p` is null for a row
+// outside the image (zero padding).
+__device__ __forceinline__ void fir_hrow(const float4* __restrict__ p, int cs, bool vl, bool vr, const float (&g)[4], float4& h0, float4& h1) {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    h0 = z; h1 = z;
+    if (!p) return;
+    float4 v[5];
+    v[0] = vl ? __ldg(p) : z;
+    v[1] = __ldg(p + cs); v[2] = __ldg(p + 2 * cs); v[3] = __ldg(p + 3 * cs);
+    v[4] = vr ? __ldg(p + 4 * cs) : z;
+    h0 = f4_scale(g[0], v[0]); h1 = f4_scale(g[0], v[1]);
+#pragma unroll
+    for (int fx = 1; fx < 4; ++fx) { h0 = f4_fma(g[fx], v[fx], h0); h1 = f4_fma(g[fx], v[fx + 1], h1); }
+}
+
+// thread = (image, strip of S vertically adjacent 2x2 output blocks, block column, 4-channel group).  The 4x4 FIR is separable
+// ([1,3,3,1]/8 * 2 per axis).  A 2x2 output block needs 5 raw rows x 5 raw columns; consecutive blocks of the strip share 3 of
+// the 5 rows, so the horizontally filtered rows are kept in registers and slid down the strip: 10 float4 loads per 4 outputs
+// instead of 25 (the unshared form is bound by L2->L1 traffic, 2.5x the raw tensor).
+__global__ void __launch_bounds__(256) fir_up_epilogue_kernel(const float* __restrict__ raw, int N, int H2, int W2, int C, int S, EpiParams E) {
+    const int RH = H2 + 1, RW = W2 + 1, c4n = C >> 2, BH = H2 >> 1, BW = W2 >> 1, nstrip = (BH + S - 1) / S;
+    const int64_t total = (int64_t)N * nstrip * BW * c4n;
+    const int64_t rstride = (int64_t)RW * c4n;                  // raw row stride in float4
     const float g[4] = {0.25f, 0.75f, 0.75f, 0.25f};
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int c4 = (int)(i % c4n);
         int64_t t = i / c4n;
         const int bx = (int)(t % BW); t /= BW;
-        const int by = (int)(t % BH);
-        const int n = (int)(t / BH);
-        const int y0 = by * 2, x0 = bx * 2;
-        float4 acc[2][2];
+        const int st = (int)(t % nstrip);
+        const int n = (int)(t / nstrip);
+        const int x0 = bx * 2, c0 = c4 * 4;
+        const int by_begin = st * S, by_end = min(by_begin + S, BH);
+        const bool vl = x0 > 0, vr = x0 + 3 < RW;              // raw columns x0-1 .. x0+3
+        // float4 pointer to raw(n, row 0, column x0-1, c0); rows are addressed relative to it
+        const float4* col = reinterpret_cast<const float4*>(raw) + ((int64_t)n * RH * RW + (x0 - 1)) * c4n + c4;
+        auto rowp = [&](int ry) -> const float4* { return (ry >= 0 && ry < RH) ? col + ry * rstride : nullptr; };
+        const EpiVec V = epi_load(E, n, C, c0);
+        const float* nzp = E.noise ? E.noise + (int64_t)n * E.noise_nstride + x0 : nullptr;
+        float4 h[5][2];
 #pragma unroll
-        for (int a = 0; a < 2; ++a)
+        for (int r = 0; r < 3; ++r) fir_hrow(rowp(2 * by_begin - 1 + r), c4n, vl, vr, g, h[r][0], h[r][1]);
+        EpiCursor P = epi_cursor(E, ((int64_t)n * H2 + 2 * by_begin) * W2 + x0, c0);
+        const int64_t adv_f32 = 2 * (int64_t)W2 * E.f32_cstride, adv0 = 2 * (int64_t)W2 * E.out[0].cstride, adv1 = 2 * (int64_t)W2 * E.out[1].cstride;
+        for (int by = by_begin; by < by_end; ++by, P.f32 += adv_f32, P.sp[0] += adv0, P.sp[1] += adv1) {
+            const int y0 = by * 2;
+            fir_hrow(rowp(y0 + 2), c4n, vl, vr, g, h[3][0], h[3][1]);
+            fir_hrow(rowp(y0 + 3), c4n, vl, vr, g, h[4][0], h[4][1]);
+            float nz[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+            if (nzp) {
 #pragma unroll
-            for (int b = 0; b < 2; ++b) acc[a][b] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int r = 0; r < 5; ++r) {
-            const int ry = y0 - 1 + r;
-            if (ry < 0 || ry >= RH) continue;
-            float4 v[5];
-#pragma unroll
-            for (int cidx = 0; cidx < 5; ++cidx) {
-                const int rx = x0 - 1 + cidx;
-                v[cidx] = (rx >= 0 && rx < RW) ? __ldg(reinterpret_cast<const float4*>(raw + (((int64_t)n * RH + ry) * RW + rx) * C) + c4)
-                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int a = 0; a < 2; ++a) {
+                    nz[a][0] = E.gain * __ldg(nzp + (int64_t)(y0 + a) * W2); nz[a][1] = E.gain * __ldg(nzp + (int64_t)(y0 + a) * W2 + 1);
+                }
             }
-            float4 h0 = f4_scale(g[0], v[0]), h1 = f4_scale(g[0], v[1]);
 #pragma unroll
-            for (int fx = 1; fx < 4; ++fx) { h0 = f4_fma(g[fx], v[fx], h0); h1 = f4_fma(g[fx], v[fx + 1], h1); }
-            if (r < 4) { acc[0][0] = f4_fma(g[r], h0, acc[0][0]); acc[0][1] = f4_fma(g[r], h1, acc[0][1]); }
-            if (r > 0) { acc[1][0] = f4_fma(g[r - 1], h0, acc[1][0]); acc[1][1] = f4_fma(g[r - 1], h1, acc[1][1]); }
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    float4 acc = f4_scale(g[0], h[a][b]);
+#pragma unroll
+                    for (int r = 1; r < 4; ++r) acc = f4_fma(g[r], h[a + r][b], acc);
+                    epi_store(E, V, P, acc, nz[a][b], a * W2 + b);
+                }
+#pragma unroll
+            for (int r = 0; r < 3; ++r) { h[r][0] = h[r + 2][0]; h[r][1] = h[r + 2][1]; }
         }
-        const int c0 = c4 * 4;
-#pragma unroll
-        for (int a = 0; a < 2; ++a)
-#pragma unroll
-            for (int b = 0; b < 2; ++b) epi_store(E, acc[a][b], n, y0 + a, x0 + b, H2, W2, C, c0);
     }
 }
 
+// Same for the down path, where the window starts two columns left of x0 (input columns x0-2 .. x0+2, x0 even in [0, W]): the
+// first two are outside together (x0 == 0: vl), the next two together (x0 == W: vm), the last one when x0 + 2 >= W (vr).
+__device__ __forceinline__ void fir_hrow_down(const float4* __restrict__ p, int cs, bool vl, bool vm, bool vr, const float (&g)[4], float4& h0, float4& h1) {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    h0 = z; h1 = z;
+    if (!p) return;
+    float4 v[5];
+    v[0] = vl ? __ldg(p) : z; v[1] = vl ? __ldg(p + cs) : z;
+    v[2] = vm ? __ldg(p + 2 * cs) : z; v[3] = vm ? __ldg(p + 3 * cs) : z;
+    v[4] = vr ? __ldg(p + 4 * cs) : z;
+    h0 = f4_scale(g[0], v[0]); h1 = f4_scale(g[0], v[1]);
+#pragma unroll
+    for (int fx = 1; fx < 4; ++fx) { h0 = f4_fma(g[fx], v[fx], h0); h1 = f4_fma(g[fx], v[fx + 1], h1); }
+}
+
 // FIR (pad 2,2,2,2) -> [(H+1),(W+1)] -> parity-split bf16 hi/lo, layout [4 parities][N][SH][SW][C].
-// thread = (sub-pixel (sy,sx), 4-channel group) -> the 2x2 block of FIR outputs (2sy+a, 2sx+b), one per parity image; separable
-// row streaming as above (25 loads per 4 outputs).
-__global__ void __launch_bounds__(256) fir_down_split_kernel(const float* __restrict__ x, int N, int H, int W, int C,
+// thread = (image, strip of S sub-pixel rows, sub-pixel column sx, 4-channel group) -> per sub-pixel the 2x2 block of FIR outputs
+// (2sy+a, 2sx+b), one per parity image; same register-resident sliding window over the horizontally filtered rows as above.
+__global__ void __launch_bounds__(256) fir_down_split_kernel(const float* __restrict__ x, int N, int H, int W, int C, int S,
                                                              __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
-    const int SH = (H + 2) / 2, SW = (W + 2) / 2, c4n = C >> 2;
-    const int64_t total = (int64_t)N * SH * SW * c4n;
+    const int SH = (H + 2) / 2, SW = (W + 2) / 2, c4n = C >> 2, nstrip = (SH + S - 1) / S;
+    const int64_t total = (int64_t)N * nstrip * SW * c4n;
     const int64_t par_stride = (int64_t)N * SH * SW * C;
     const float g[4] = {0.125f, 0.375f, 0.375f, 0.125f};
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int c4 = (int)(i % c4n);
         int64_t t = i / c4n;
         const int sx = (int)(t % SW); t /= SW;
-        const int sy = (int)(t % SH);
-        const int n = (int)(t / SH);
-        const int y0 = sy * 2, x0 = sx * 2;                  // FIR output (y, x) reads input rows y-2 .. y+1
-        float4 acc[2][2];
+        const int st = (int)(t % nstrip);
+        const int n = (int)(t / nstrip);
+        const int x0 = sx * 2;                               // FIR output (y, x) reads input rows y-2 .. y+1, columns x-2 .. x+1
+        const int sy_begin = st * S, sy_end = min(sy_begin + S, SH);
+        const bool vl = x0 >= 2, vm = x0 < W, vr = x0 + 2 < W;
+        const float4* col = reinterpret_cast<const float4*>(x) + ((int64_t)n * H * W + (x0 - 2)) * c4n + c4;
+        const int64_t rstride = (int64_t)W * c4n;
+        auto rowp = [&](int iy) -> const float4* { return (iy >= 0 && iy < H) ? col + iy * rstride : nullptr; };
+        float4 h[5][2];
 #pragma unroll
-        for (int a = 0; a < 2; ++a)
+        for (int r = 0; r < 3; ++r) fir_hrow_down(rowp(2 * sy_begin - 2 + r), c4n, vl, vm, vr, g, h[r][0], h[r][1]);
+        for (int sy = sy_begin; sy < sy_end; ++sy) {
+            const int y0 = sy * 2;
+            fir_hrow_down(rowp(y0 + 1), c4n, vl, vm, vr, g, h[3][0], h[3][1]);
+            fir_hrow_down(rowp(y0 + 2), c4n, vl, vm, vr, g, h[4][0], h[4][1]);
+            const int64_t o = (((int64_t)n * SH + sy) * SW + sx) * C + c4 * 4;
 #pragma unroll
-            for (int b = 0; b < 2; ++b) acc[a][b] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int a = 0; a < 2; ++a)
 #pragma unroll
-        for (int r = 0; r < 5; ++r) {
-            const int iy = y0 - 2 + r;
-            if (iy < 0 || iy >= H) continue;
-            float4 v[5];
+                for (int b = 0; b < 2; ++b) {
+                    float4 v = f4_scale(g[0], h[a][b]);
 #pragma unroll
-            for (int cidx = 0; cidx < 5; ++cidx) {
-                const int ix = x0 - 2 + cidx;
-                v[cidx] = (ix >= 0 && ix < W) ? __ldg(reinterpret_cast<const float4*>(x + (((int64_t)n * H + iy) * W + ix) * C) + c4)
-                                              : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            float4 h0 = f4_scale(g[0], v[0]), h1 = f4_scale(g[0], v[1]);
+                    for (int r = 1; r < 4; ++r) v = f4_fma(g[r], h[a + r][b], v);
+                    if (y0 + a > H || x0 + b > W) v = make_float4(0.f, 0.f, 0.f, 0.f);     // beyond the (H+1)x(W+1) FIR output: zero pad
+                    uint2 hh, l;
+                    split_bf16x2(v.x, v.y, hh.x, l.x); split_bf16x2(v.z, v.w, hh.y, l.y);
+                    const int64_t off = (int64_t)(a * 2 + b) * par_stride + o;
+                    *reinterpret_cast<uint2*>(hi + off) = hh;
+                    *reinterpret_cast<uint2*>(lo + off) = l;
+                }
 #pragma unroll
-            for (int fx = 1; fx < 4; ++fx) { h0 = f4_fma(g[fx], v[fx], h0); h1 = f4_fma(g[fx], v[fx + 1], h1); }
-            if (r < 4) { acc[0][0] = f4_fma(g[r], h0, acc[0][0]); acc[0][1] = f4_fma(g[r], h1, acc[0][1]); }
-            if (r > 0) { acc[1][0] = f4_fma(g[r - 1], h0, acc[1][0]); acc[1][1] = f4_fma(g[r - 1], h1, acc[1][1]); }
+            for (int r = 0; r < 3; ++r) { h[r][0] = h[r + 2][0]; h[r][1] = h[r + 2][1]; }
         }
-        const int64_t o = (((int64_t)n * SH + sy) * SW + sx) * C + c4 * 4;
-#pragma unroll
-        for (int a = 0; a < 2; ++a)
-#pragma unroll
-            for (int b = 0; b < 2; ++b) {
-                float4 v = acc[a][b];
-                if (y0 + a > H || x0 + b > W) v = make_float4(0.f, 0.f, 0.f, 0.f);     // beyond the (H+1)x(W+1) FIR output: zero pad
-                __nv_bfloat16 h[4], l[4];
-                split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]); split_bf16(v.z, h[2], l[2]); split_bf16(v.w, h[3], l[3]);
-                const int64_t off = (int64_t)(a * 2 + b) * par_stride + o;
-                *reinterpret_cast<uint2*>(hi + off) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
-                *reinterpret_cast<uint2*>(lo + off) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
-            }
     }
 }
 
@@ -338,6 +410,15 @@ extern "C" int n3d_demod(const float* styles, const float* wsq, const int64_t* r
     return N3D_OK;
 }
 
+// Rows per thread strip of the FIR kernels: 16 (3 re-read halo rows per strip) for launches with >= 1024 threads per SM, halved
+// down to 4 for smaller ones.  Measured on B200 (tools/bench_layers.py): S=1 is 1.3-1.6x slower than S=4 at every size, S=64
+// loses on everything below 256^2.
+static int fir_strip_rows(int64_t threads_per_row, int rows) {
+    int S = 16;
+    while (S > 4 && threads_per_row * n3d_div_up(rows, S) < (int64_t)148 * 1024) S >>= 1;
+    return min(S, rows);
+}
+
 extern "C" int n3d_modulate_split(const float* x, int64_t npix_per_img, int N, int C, const float* style, void* hi, void* lo,
                                   int out_cstride, int out_coff, void* stream) {
     N3D_CHECK_ARG(x && hi && lo, "n3d_modulate_split: null pointer");
@@ -354,6 +435,7 @@ extern "C" int n3d_fir_up_epilogue(const float* raw, int N, int H2, int W2, int 
                                    const N3DSplitOut out[2], float* out_f32, int f32_cstride, int f32_coff, void* stream) {
     N3D_CHECK_ARG(raw && out, "n3d_fir_up_epilogue: null pointer");
     N3D_CHECK_ARG(C % 4 == 0, "n3d_fir_up_epilogue: C must be a multiple of 4");
+    N3D_CHECK_ARG(gain > 0.f && slope >= 0.f && slope <= 1.f, "n3d_fir_up_epilogue: needs gain > 0 and 0 <= slope <= 1 (lrelu / linear)");
     EpiParams E;
     E.dcoef = dcoef; E.bias = bias; E.noise = noise; E.noise_nstride = noise_nstride; E.gain = gain; E.slope = slope; E.clamp = clamp;
     E.out[0] = out[0]; E.out[1] = out[1]; E.out_f32 = out_f32; E.f32_cstride = f32_cstride; E.f32_coff = f32_coff;
@@ -361,8 +443,9 @@ extern "C" int n3d_fir_up_epilogue(const float* raw, int N, int H2, int W2, int 
         N3D_CHECK_ARG(!E.out[k].hi || ((E.out[k].cstride % 4 == 0) && (E.out[k].coff % 4 == 0)), "n3d_fir_up_epilogue: unaligned split output");
     N3D_CHECK_ARG(!out_f32 || (f32_cstride % 4 == 0 && f32_coff % 4 == 0), "n3d_fir_up_epilogue: unaligned fp32 output");
     N3D_CHECK_ARG(H2 % 2 == 0 && W2 % 2 == 0, "n3d_fir_up_epilogue: output size must be even");
-    const int64_t total = (int64_t)N * (H2 / 2) * (W2 / 2) * (C / 4);
-    fir_up_epilogue_kernel<<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(raw, N, H2, W2, C, E);
+    const int S = fir_strip_rows((int64_t)N * (W2 / 2) * (C / 4), H2 / 2);
+    const int64_t total = (int64_t)N * n3d_div_up(H2 / 2, S) * (W2 / 2) * (C / 4);
+    fir_up_epilogue_kernel<<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(raw, N, H2, W2, C, S, E);
     N3D_CHECK_LAUNCH("n3d_fir_up_epilogue");
     return N3D_OK;
 }
@@ -370,8 +453,9 @@ extern "C" int n3d_fir_up_epilogue(const float* raw, int N, int H2, int W2, int 
 extern "C" int n3d_fir_down_split(const float* x, int N, int H, int W, int C, void* hi, void* lo, void* stream) {
     N3D_CHECK_ARG(x && hi && lo, "n3d_fir_down_split: null pointer");
     N3D_CHECK_ARG(C % 4 == 0 && H % 2 == 0 && W % 2 == 0, "n3d_fir_down_split: C %% 4 and even H, W required");
-    const int64_t total = (int64_t)N * ((H + 2) / 2) * ((W + 2) / 2) * (C / 4);
-    fir_down_split_kernel<<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(x, N, H, W, C, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+    const int S = fir_strip_rows((int64_t)N * ((W + 2) / 2) * (C / 4), (H + 2) / 2);
+    const int64_t total = (int64_t)N * n3d_div_up((H + 2) / 2, S) * ((W + 2) / 2) * (C / 4);
+    fir_down_split_kernel<<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(x, N, H, W, C, S, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
     N3D_CHECK_LAUNCH("n3d_fir_down_split");
     return N3D_OK;
 }

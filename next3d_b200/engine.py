@@ -88,6 +88,7 @@ class Engine:
         L = _ModLayer(name, cin, cout, k, up, widx, is_rgb, clamp)
         w = sd[f'{name}.weight'].float()
         L.w_hi, L.w_lo = K.pack_conv_weight(w)
+        L.w_f32 = w.reshape(cout, cin).contiguous() if (is_rgb and cout <= 4) else None    # fused-ToRGB epilogue operand
         L.bias = sd[f'{name}.bias'].float().contiguous()
         L.aff_w = sd[f'{name}.affine.weight'].float().contiguous()
         L.aff_b = sd[f'{name}.affine.bias'].float().contiguous()
@@ -259,7 +260,13 @@ class Engine:
         return K.make_split_out(buf.hi, buf.lo, style, buf.C, coff)
 
     # ------------------------------------------------------------------------------------------ layer runners
-    def _modconv(self, name, a, res_in, outs, noise_mode, f32=None):
+    def _fused_rgb(self, name, img, accumulate, nchw=False):
+        """Descriptor that folds ToRGBLayer `name` (<= 4 image channels) into the epilogue of the conv producing its input."""
+        L = self.mod[name]
+        return dict(out=img, weight=L.w_f32, style=self._style(L), bias=L.bias, clamp=L.clamp if L.clamp is not None else -1.0,
+                    nchw=nchw, accumulate=accumulate)
+
+    def _modconv(self, name, a, res_in, outs, noise_mode, f32=None, rgb=None):
         """SynthesisLayer (networks_stylegan2.py:311-330); `a` already carries this layer's modulation."""
         L, N = self.mod[name], self._N
         self._cur_layer = name
@@ -268,9 +275,10 @@ class Engine:
         if L.up == 1:
             self._gemm(a.hi, a.lo, L.w_hi, L.w_lo, K.taps_conv3x3(), N, res_in, res_in, nprod=self.nprod, dcoef=self._dcoef(L), bias=L.bias,
                         noise=noise, noise_nstride=nstride, gain=SQRT2, slope=0.2, clamp=clamp, outs=outs, out_f32=f32,
-                        f32_cstride=L.cout if f32 is not None else 0)
+                        f32_cstride=L.cout if f32 is not None else 0, rgb=rgb)
             self.launches += 1
             return
+        assert rgb is None
         raw = self._f32(N, 2 * res_in + 1, 2 * res_in + 1, L.cout)
         flops = 2.0 * L.cin * L.cout * N * (3 * res_in + 2) ** 2          # taps x positions summed over the 4 parity classes
         self.conv_flops += flops
@@ -450,24 +458,21 @@ class Engine:
         res0 = r0 * (2 if cfg.sr_module == '8XDC' else 1)
         x1 = Split((N, res0, res0, c0), dev)
         self._modconv(f'{p0}.conv0', x, r0, [self._out(x1, f'{p0}.conv1')], noise_mode_sr)
-        rgb_in = Split((N, res0, res0, c0), dev)
         x2 = Split((N, res0, res0, c0), dev)
-        self._modconv(f'{p0}.conv1', x1, res0, [self._out(rgb_in, f'{p0}.torgb'), self._out(x2, f'{p1}.conv0')], noise_mode_sr)
         if cfg.sr_module == '8XDC':
             img = self._f32(N, res0, res0, 3)
             K.upsample2d_nhwc(rgb, img)
             self.launches += 1
         else:
             img = rgb.clone()                                                   # SynthesisBlockNoUp: no image upsample
-        self._torgb(f'{p0}.torgb', rgb_in, res0, img, accumulate=True)
+        # the two ToRGB layers (3 channels) run inside the conv1 epilogues: img += torgb(conv1 output)
+        self._modconv(f'{p0}.conv1', x1, res0, [self._out(x2, f'{p1}.conv0')], noise_mode_sr, rgb=self._fused_rgb(f'{p0}.torgb', img, True))
         # block1
         res1 = res0 * 2
         x3 = Split((N, res1, res1, c1), dev)
         self._modconv(f'{p1}.conv0', x2, res0, [self._out(x3, f'{p1}.conv1')], noise_mode_sr)
-        rgb_in1 = Split((N, res1, res1, c1), dev)
-        self._modconv(f'{p1}.conv1', x3, res1, [self._out(rgb_in1, f'{p1}.torgb')], noise_mode_sr)
         K.upsample2d_nhwc(img, image_out, y_nchw=True)
-        self._torgb(f'{p1}.torgb', rgb_in1, res1, image_out, accumulate=True, nchw=True)
+        self._modconv(f'{p1}.conv1', x3, res1, [], noise_mode_sr, rgb=self._fused_rgb(f'{p1}.torgb', image_out, True, nchw=True))
         self.launches += 1
 
     # ------------------------------------------------------------------------------------------ planes + synthesis

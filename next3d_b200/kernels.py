@@ -54,7 +54,7 @@ def make_split_out(hi=None, lo=None, style=None, cstride=0, coff=0):
 # ------------------------------------------------------------------------------------------------ kernels
 def conv_gemm(a_hi, a_lo, w_hi, w_lo, taps, N, MH, MW, *, a_img_mul=0, nprod=3, mode=0, dcoef=None, bias=None, noise=None,
               noise_nstride=0, gain=1.0, slope=1.0, clamp=-1.0, outs=(), out_f32=None, f32_cstride=0, f32_coff=0, f32_nchw=False,
-              f32_accumulate=False, oy_mul=1, oy_off=0, ox_mul=1, ox_off=0, OH=None, OW=None):
+              f32_accumulate=False, oy_mul=1, oy_off=0, ox_mul=1, ox_off=0, OH=None, OW=None, rgb=None):
     """a_*: bf16 [NI, AH, AW, Cin]; w_*: bf16 [T, Cout, Cin]; taps: list of (dy, dx, img_off, wtap)."""
     NI, AH, AW, Cin = a_hi.shape
     T, Cout, Cin_w = w_hi.shape
@@ -78,6 +78,9 @@ def conv_gemm(a_hi, a_lo, w_hi, w_lo, taps, N, MH, MW, *, a_img_mul=0, nprod=3, 
     p.oy_mul, p.oy_off, p.ox_mul, p.ox_off = oy_mul, oy_off, ox_mul, ox_off
     p.OH = OH if OH is not None else MH * oy_mul
     p.OW = OW if OW is not None else MW * ox_mul
+    if rgb is not None:                                  # dict(out, weight [c,Cout], style [N,Cout], bias [c], clamp, nchw, accumulate)
+        p.rgb = _lib.FusedRgb(ptr(rgb['out']), ptr(rgb['weight']), ptr(rgb['style']), ptr(rgb['bias']), float(rgb.get('clamp', -1.0)),
+                              rgb['weight'].shape[0], int(rgb.get('nchw', False)), int(rgb.get('accumulate', False)))
     check(lib.n3d_conv_gemm(C.byref(p), stream_ptr()), 'n3d_conv_gemm')
 
 

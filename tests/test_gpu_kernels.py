@@ -114,6 +114,38 @@ def test_conv1x1_torgb_nchw_accumulate(K):
     assert range_rel_err(out.cpu(), ref) < 3e-5
 
 
+@pytest.mark.parametrize('N,Cin,Cout,res,nchw,with_out', [(2, 64, 128, 32, True, True), (1, 128, 256, 16, False, True), (2, 32, 128, 32, True, False)])
+def test_conv_fused_torgb(K, N, Cin, Cout, res, nchw, with_out):
+    """ToRGBLayer (networks_stylegan2.py:353-357) folded into the producing conv's epilogue: img += clamp(W_rgb (y * s_rgb) + b_rgb),
+    optionally with no other output of the conv at all (last super-resolution layer)."""
+    g = _g(19 + Cout + res)
+    x = torch.randn(N, Cin, res, res, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(Cin * 9)
+    d = torch.rand(N, Cout, generator=g) + 0.5
+    b = torch.randn(Cout, generator=g)
+    s_next = torch.randn(N, Cout, generator=g)
+    s_rgb = torch.randn(N, Cout, generator=g) / math.sqrt(Cout)
+    w_rgb = torch.randn(3, Cout, generator=g)
+    b_rgb = torch.randn(3, generator=g)
+    prev = torch.randn(N, 3, res, res, generator=g)
+    y = (F.leaky_relu(F.conv2d(x, w, padding=1) * d[:, :, None, None] + b[None, :, None, None], 0.2) * math.sqrt(2)).clamp(-256, 256)
+    rgb = torch.einsum('nchw,nc,kc->nkhw', y.double(), s_rgb.double(), w_rgb.double()).float() + b_rgb[None, :, None, None]
+    ref = prev + rgb.clamp(-2.0, 2.0)
+    a_hi, a_lo = _nhwc_split(K, x)
+    w_hi, w_lo = K.pack_conv_weight(w.to(DEV))
+    img = (prev if nchw else prev.permute(0, 2, 3, 1)).contiguous().to(DEV)
+    o_hi = torch.zeros(N, res, res, Cout, device=DEV, dtype=torch.bfloat16)
+    o_lo = torch.zeros_like(o_hi)
+    dd, bd, sn, sr, wr, br = d.to(DEV), b.to(DEV), s_next.to(DEV), s_rgb.to(DEV), w_rgb.to(DEV), b_rgb.to(DEV)
+    K.conv_gemm(a_hi, a_lo, w_hi, w_lo, K.taps_conv3x3(), N, res, res, dcoef=dd, bias=bd, gain=math.sqrt(2), slope=0.2, clamp=256.0,
+                outs=[K.make_split_out(o_hi, o_lo, sn, Cout, 0)] if with_out else [],
+                rgb=dict(out=img, weight=wr, style=sr, bias=br, clamp=2.0, nchw=nchw, accumulate=True))
+    got = img.cpu() if nchw else img.permute(0, 3, 1, 2).cpu()
+    assert range_rel_err(got, ref) < 5e-5
+    if with_out:
+        assert range_rel_err(_join(o_hi, o_lo).permute(0, 3, 1, 2).cpu(), y * s_next[:, :, None, None]) < 5e-5
+
+
 @pytest.mark.parametrize('N,Cin,Cout,res', [(2, 64, 64, 8), (1, 512, 512, 4), (1, 32, 256, 32), (2, 128, 64, 16)])
 def test_upconv_modulated(K, N, Cin, Cout, res):
     """4 transposed-conv parity GEMMs + FIR epilogue == the reference's up=2 modulated conv + bias_act (oracle)."""
