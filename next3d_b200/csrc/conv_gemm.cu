@@ -13,6 +13,7 @@
 //   warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> fused demod/noise/bias/lrelu/clamp ->
 //   next layer's modulation -> bf16 split / fp32 stores).  Two TMEM accumulator buffers overlap the epilogue of
 //   tile i with the MMAs of tile i+1.
+#include <cstdlib>
 #include "common.cuh"
 #include "../../include/next3d_b200.h"
 #include <cuda.h>
@@ -36,6 +37,7 @@ struct KParams {
     // up to 4 sub-problems sharing operands / tile shape / epilogue (the 4 output-parity classes of a stride-2 transposed conv)
     int nsub;
     struct Sub { int tap_begin, ntaps, MH, MW, tiles_x, tiles_y, oy_off, ox_off, tile_end; } sub[4];
+    int pair, tile_h, acc_half;        // pair = 1: a CTA tile is two vertically stacked 128-row sub-tiles (M = 256) sharing one weight tile
     int block_n, acc_stride, tmem_cols, stages, stage_bytes, b_bytes, a_bytes, block_k;
     int cin_chunks, ntaps, nprod, a_img_stride;
     N3DConvTap taps[9];
@@ -64,7 +66,7 @@ __device__ __forceinline__ TileInfo decode_tile(const KParams& P, int tile) {
     t.tn = local % P.tiles_n;
     const int tm = local / P.tiles_n, tx = P.sub[sidx].tiles_x, ty = P.sub[sidx].tiles_y;
     t.x0 = (tm % tx) * P.TW;
-    t.y0 = ((tm / tx) % ty) * P.TH;
+    t.y0 = ((tm / tx) % ty) * P.tile_h;
     t.n0 = (tm / (tx * ty)) * P.TN;
     return t;
 }
@@ -157,12 +159,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                     tc_fence_after();
                     const uint32_t sa = smem_base + (uint32_t)s * (uint32_t)P.stage_bytes;
                     const uint32_t a_hi = sa, a_lo = sa + (uint32_t)P.a_bytes, b_hi = sa + 2u * (uint32_t)P.a_bytes, b_lo = b_hi + (uint32_t)P.b_bytes;
-                    for (int k = 0; k < k16; ++k) {
-                        const uint32_t koff = (uint32_t)k * 32u;     // 16 bf16 = 32 bytes inside the swizzle row
-                        umma_bf16(d_tmem, umma_desc(a_hi + koff, dhi), umma_desc(b_hi + koff, dhi), idesc, (ks | k) != 0);
-                        if (P.nprod == 3) {
-                            umma_bf16(d_tmem, umma_desc(a_hi + koff, dhi), umma_desc(b_lo + koff, dhi), idesc, 1u);
-                            umma_bf16(d_tmem, umma_desc(a_lo + koff, dhi), umma_desc(b_hi + koff, dhi), idesc, 1u);
+                    for (int u = 0; u <= P.pair; ++u) {            // pair mode: both sub-tiles consume the same weight tile
+                        const uint32_t du = d_tmem + (uint32_t)(u * P.acc_half), au = (uint32_t)u * (uint32_t)(kBlockM * P.block_k * 2);
+                        for (int k = 0; k < k16; ++k) {
+                            const uint32_t koff = (uint32_t)k * 32u;     // 16 bf16 = 32 bytes inside the swizzle row
+                            umma_bf16(du, umma_desc(a_hi + au + koff, dhi), umma_desc(b_hi + koff, dhi), idesc, (ks | k) != 0);
+                            if (P.nprod == 3) {
+                                umma_bf16(du, umma_desc(a_hi + au + koff, dhi), umma_desc(b_lo + koff, dhi), idesc, 1u);
+                                umma_bf16(du, umma_desc(a_lo + au + koff, dhi), umma_desc(b_hi + koff, dhi), idesc, 1u);
+                            }
                         }
                     }
                     umma_commit(empty_bar(s));                 // frees the smem stage once these MMAs retire
@@ -190,13 +195,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             ++cnt;
             if (!mine) continue;
             const int tn = ti.tn, n0 = ti.n0;
-            const int x = ti.x0 + tw, y = ti.y0 + th;
+            const int x = ti.x0 + tw;
             const int n = n0 + tnn;
-            const int oy = y * P.oy_mul + P.sub[ti.sub].oy_off, ox = x * P.ox_mul + P.sub[ti.sub].ox_off;
-            const bool valid = (n < P.N) && (y < P.sub[ti.sub].MH) && (x < P.sub[ti.sub].MW) && (oy < P.OH) && (ox < P.OW);
-            const int64_t opix = ((int64_t)n * P.OH + oy) * P.OW + ox;
-            float nz = 0.f;
-            if (valid && P.noise) nz = __ldg(P.noise + (int64_t)n * P.noise_nstride + (int64_t)oy * P.OW + ox);
+            const int ox = x * P.ox_mul + P.sub[ti.sub].ox_off;
             if (staged) {
                 // all 4 warps of the group are done with the previous tile's vectors before they are overwritten
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
@@ -220,7 +221,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 
             mbar_wait(tfull_bar(g), acc_ph, P.err_flag, 4);
             tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * P.acc_stride);
+            for (int u = 0; u <= P.pair; ++u) {
+            const int y = ti.y0 + u * P.TH + th;
+            const int oy = y * P.oy_mul + P.sub[ti.sub].oy_off;
+            const bool valid = (n < P.N) && (y < P.sub[ti.sub].MH) && (x < P.sub[ti.sub].MW) && (oy < P.OH) && (ox < P.OW);
+            const int64_t opix = ((int64_t)n * P.OH + oy) * P.OW + ox;
+            float nz = 0.f;
+            if (valid && P.noise) nz = __ldg(P.noise + (int64_t)n * P.noise_nstride + (int64_t)oy * P.OW + ox);
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * P.acc_stride + u * P.acc_half);
             float racc[4] = {0.f, 0.f, 0.f, 0.f};
             for (int c16 = 0; c16 < P.block_n; c16 += 16) {
                 uint32_t r[16];
@@ -295,7 +303,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                         for (int j = 0; j < 16; ++j) if (j < nco) dst[j * cs] = v[j];
                     } else {
                         float* dst = P.out_f32 + opix * P.f32_cstride + P.f32_coff + co0;
-                        if (nco == 16 && (((P.f32_cstride | (P.f32_coff + co0)) & 3) == 0)) {
+                        if (nco == 16 && (((uintptr_t)dst & 31) == 0)) {                 // two full 32-byte sectors per thread
+                            if (P.f32_accumulate) {
+                                float old[16];
+                                ld_global_256(dst, old); ld_global_256(dst + 8, old + 8);
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) v[j] += old[j];
+                            }
+                            st_global_256(dst, v); st_global_256(dst + 8, v + 8);
+                        } else if (nco == 16 && (((P.f32_cstride | (P.f32_coff + co0)) & 3) == 0)) {
                             if (P.f32_accumulate) {
                                 float4 old[4];
 #pragma unroll
@@ -329,7 +345,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                         split_bf16x2(v[2 * j] * (k == 0 ? s0[2 * j] : s1[2 * j]), v[2 * j + 1] * (k == 0 ? s0[2 * j + 1] : s1[2 * j + 1]), h[j], l[j]);
                     __nv_bfloat16* dh = (__nv_bfloat16*)o.hi + opix * o.cstride + o.coff + co0;
                     __nv_bfloat16* dl = (__nv_bfloat16*)o.lo + opix * o.cstride + o.coff + co0;
-                    if (nco == 16 && (((o.cstride | (o.coff + co0)) & 7) == 0)) {
+                    if (nco == 16 && ((((uintptr_t)dh | (uintptr_t)dl) & 31) == 0)) {           // one full 32-byte sector per array
+                        st_global_256(dh, h); st_global_256(dl, l);
+                    } else if (nco == 16 && (((o.cstride | (o.coff + co0)) & 7) == 0)) {
 #pragma unroll
                         for (int j = 0; j < 8; j += 4) {
                             *reinterpret_cast<uint4*>(dh + 2 * j) = make_uint4(h[j], h[j + 1], h[j + 2], h[j + 3]);
@@ -356,6 +374,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                     }
                 }
             }
+            }   // u
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(g));
@@ -467,10 +486,25 @@ int launch_conv(const N3DConvGemm* p, int nsub, const SubSpec* specs, void* stre
     }
     K.block_n = bn;
     K.tiles_n = n3d_div_up(p->Cout, bn);
-    K.acc_stride = max(32, pow2_ceil(bn));
+    // Pair mode (M = 256 per CTA tile): with block_n = 128 the kernel is bound by the L2 -> shared-memory fill rate (measured
+    // 12.3 TB/s chip-wide, profiles/r01_ncu_convsr.txt), not by the tensor pipe; two sub-tiles sharing each weight tile cut the
+    // bytes per MMA by 25 %.  Only for launches with several waves of tiles.
+    K.pair = (bn == 128 && K.TN == 1 && tiles_m * K.tiles_n >= 8 * 148) ? 1 : 0;
+    {
+        static int force = -2;
+        if (force == -2) { const char* e = getenv("N3D_CONV_PAIR"); force = e ? atoi(e) : -1; }
+        if (force == 0) K.pair = 0;
+    }
+    K.tile_h = K.TH * (1 + K.pair);
+    if (K.pair) {
+        tiles_m = 0;
+        for (int i = 0; i < nsub; ++i) { K.sub[i].tiles_y = n3d_div_up(specs[i].MH, K.tile_h); tiles_m += K.sub[i].tiles_x * K.sub[i].tiles_y * K.tiles_i; }
+    }
+    K.acc_half = max(32, pow2_ceil(bn));
+    K.acc_stride = K.acc_half * (1 + K.pair);
     K.tmem_cols = 2 * K.acc_stride;
     K.block_k = (p->Cin % 64 == 0 || p->Cin % 32 != 0) ? 64 : 32;
-    K.a_bytes = kBlockM * K.block_k * 2;
+    K.a_bytes = (1 + K.pair) * kBlockM * K.block_k * 2;
     K.b_bytes = bn * K.block_k * 2;
     K.stage_bytes = 2 * K.a_bytes + 2 * K.b_bytes;
     K.stages = min(6, (200 * 1024) / K.stage_bytes);      // + 16 KiB epilogue staging + barriers + 1 KiB alignment slack <= 227 KiB
@@ -494,7 +528,7 @@ int launch_conv(const N3DConvGemm* p, int nsub, const SubSpec* specs, void* stre
     K.err_flag = g_err_flag;
 
     const uint64_t adims[4] = {(uint64_t)p->Cin, (uint64_t)p->AW, (uint64_t)p->AH, (uint64_t)p->NI};
-    const uint32_t abox[4] = {(uint32_t)K.block_k, (uint32_t)K.TW, (uint32_t)K.TH, (uint32_t)K.TN};
+    const uint32_t abox[4] = {(uint32_t)K.block_k, (uint32_t)K.TW, (uint32_t)K.tile_h, (uint32_t)K.TN};
     const uint64_t wdims[3] = {(uint64_t)p->Cin, (uint64_t)p->Cout, (uint64_t)p->T};
     const uint32_t wbox[3] = {(uint32_t)K.block_k, (uint32_t)bn, 1u};
     int rc;

@@ -332,46 +332,107 @@ __device__ __forceinline__ float aa_weight(const AxisTaps& t, int j) {
     return t.total != 0.f ? w / t.total : w;
 }
 
-// one warp per destination pixel; lanes stride over channels
+// Source / destination windows of image n (python slicing semantics: boxes clipped to the image).  Returns false when the
+// destination pixel (dy, dx) lies outside the paste window or a window is empty.
+struct ResizeWin { int sy0, sx0, ih, iw, ty0, tx0, oh, ow; };
+__device__ __forceinline__ bool resize_window(const int* __restrict__ src_box, const int* __restrict__ dst_box, int n, int SH, int SW, int DH, int DW,
+                                              int dy, int dx, ResizeWin& w) {
+    int sy0 = 0, sy1 = SH, sx0 = 0, sx1 = SW, ty0 = 0, ty1 = DH, tx0 = 0, tx1 = DW;
+    if (src_box) { sy0 = src_box[n * 4]; sy1 = src_box[n * 4 + 1]; sx0 = src_box[n * 4 + 2]; sx1 = src_box[n * 4 + 3]; }
+    if (dst_box) { ty0 = dst_box[n * 4]; ty1 = dst_box[n * 4 + 1]; tx0 = dst_box[n * 4 + 2]; tx1 = dst_box[n * 4 + 3]; }
+    sy0 = max(sy0, 0); sx0 = max(sx0, 0); sy1 = min(sy1, SH); sx1 = min(sx1, SW);
+    w.sy0 = sy0; w.sx0 = sx0; w.ih = sy1 - sy0; w.iw = sx1 - sx0; w.ty0 = ty0; w.tx0 = tx0; w.oh = ty1 - ty0; w.ow = tx1 - tx0;
+    if (dy < ty0 || dy >= ty1 || dx < tx0 || dx >= tx1) return false;
+    return w.ih > 0 && w.iw > 0 && w.oh > 0 && w.ow > 0;
+}
+
+__device__ __forceinline__ void resize_store(float acc, int64_t o, int n, int C, int c, float* __restrict__ dst, const float* __restrict__ style,
+                                             __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+    if (dst) dst[o] = acc;
+    if (hi) {
+        float s = acc;
+        if (style) s *= __ldg(style + (int64_t)n * C + c);
+        __nv_bfloat16 h, l;
+        split_bf16(s, h, l);
+        hi[o] = h; lo[o] = l;
+    }
+}
+
+// Wide channels (C = 4 * 2^k <= 128): one warp per destination pixel; the lanes are split into C/4 float4 channel groups x
+// 32/(C/4) tap lanes, each tap lane walks every (32/(C/4))-th tap of the window, then the tap lanes are summed with shuffles.
+// A warp owns `ppw` consecutive destination pixels per step: their window tests run in parallel on the lanes (ballot), the
+// pixels inside are then filtered one after the other.
 __global__ void __launch_bounds__(256) resize_aa_kernel(const float* __restrict__ src, int N, int SH, int SW, int C, const int* __restrict__ src_box,
                                                         float* __restrict__ dst, int DH, int DW, const int* __restrict__ dst_box, const float* __restrict__ style,
-                                                        __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+                                                        __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int ppw) {
     const int lane = threadIdx.x & 31;
     const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int64_t total = (int64_t)N * DH * DW;
-    for (int64_t pi = warp_global; pi < total; pi += nwarps) {
-        const int n = (int)(pi / ((int64_t)DH * DW));
-        const int dy = (int)((pi / DW) % DH), dx = (int)(pi % DW);
-        int sy0 = 0, sy1 = SH, sx0 = 0, sx1 = SW, ty0 = 0, ty1 = DH, tx0 = 0, tx1 = DW;
-        if (src_box) { sy0 = src_box[n * 4]; sy1 = src_box[n * 4 + 1]; sx0 = src_box[n * 4 + 2]; sx1 = src_box[n * 4 + 3]; }
-        if (dst_box) { ty0 = dst_box[n * 4]; ty1 = dst_box[n * 4 + 1]; tx0 = dst_box[n * 4 + 2]; tx1 = dst_box[n * 4 + 3]; }
-        // python slicing semantics: clip the boxes to the image
-        sy0 = max(sy0, 0); sx0 = max(sx0, 0); sy1 = min(sy1, SH); sx1 = min(sx1, SW);
-        const int oh = ty1 - ty0, ow = tx1 - tx0;              // requested output size
-        if (dy < ty0 || dy >= ty1 || dx < tx0 || dx >= tx1 || dy >= DH || dx >= DW) continue;
-        const int ih = sy1 - sy0, iw = sx1 - sx0;
-        if (ih <= 0 || iw <= 0 || oh <= 0 || ow <= 0) continue;
-        const AxisTaps ay = aa_axis(dy - ty0, ih, oh), ax = aa_axis(dx - tx0, iw, ow);
-        for (int c = lane; c < C; c += 32) {
-            float acc = 0.f;
-            for (int j = 0; j < ay.n; ++j) {
-                const float wy = aa_weight(ay, j);
-                const float* row = src + (((int64_t)n * SH + sy0 + ay.lo + j) * SW + sx0 + ax.lo) * C + c;
-                float racc = 0.f;
-                for (int i = 0; i < ax.n; ++i) racc += aa_weight(ax, i) * __ldg(row + (int64_t)i * C);
-                acc += wy * racc;
-            }
-            const int64_t o = (((int64_t)n * DH + dy) * DW + dx) * C + c;
-            if (dst) dst[o] = acc;
-            if (hi) {
-                float s = acc;
-                if (style) s *= __ldg(style + (int64_t)n * C + c);
-                __nv_bfloat16 h, l;
-                split_bf16(s, h, l);
-                hi[o] = h; lo[o] = l;
+    const int c4n = C >> 2, ntl = 32 / c4n, tl = lane / c4n, c4 = lane - tl * c4n;
+    for (int64_t base = warp_global * ppw; base < total; base += nwarps * ppw) {
+        // lane l < ppw tests destination pixel base + l; the warp then visits the pixels that are inside their paste window
+        bool inside = false;
+        {
+            const int64_t pi = base + lane;
+            if (lane < ppw && pi < total) {
+                ResizeWin w;
+                inside = resize_window(src_box, dst_box, (int)(pi / ((int64_t)DH * DW)), SH, SW, DH, DW, (int)((pi / DW) % DH), (int)(pi % DW), w);
             }
         }
+        unsigned todo = __ballot_sync(0xffffffffu, inside);
+        while (todo) {
+            const int l = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int64_t pi = base + l;
+            const int n = (int)(pi / ((int64_t)DH * DW)), dy = (int)((pi / DW) % DH), dx = (int)(pi % DW);
+            ResizeWin w;
+            resize_window(src_box, dst_box, n, SH, SW, DH, DW, dy, dx, w);
+            const AxisTaps ay = aa_axis(dy - w.ty0, w.ih, w.oh), ax = aa_axis(dx - w.tx0, w.iw, w.ow);
+            const float4* win = reinterpret_cast<const float4*>(src + (((int64_t)n * SH + w.sy0 + ay.lo) * SW + w.sx0 + ax.lo) * C) + c4;
+            const int nt = ay.n * ax.n;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+            for (int t = tl; t < nt; t += ntl) {
+                const int j = t / ax.n, i = t - j * ax.n;
+                const float wt = aa_weight(ay, j) * aa_weight(ax, i);
+                const float4 v = __ldg(win + ((int64_t)j * SW + i) * c4n);
+                acc.x = fmaf(wt, v.x, acc.x); acc.y = fmaf(wt, v.y, acc.y); acc.z = fmaf(wt, v.z, acc.z); acc.w = fmaf(wt, v.w, acc.w);
+            }
+            for (int off = c4n; off < 32; off <<= 1) {
+                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+                acc.z += __shfl_xor_sync(0xffffffffu, acc.z, off); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, off);
+            }
+            if (tl == 0) {
+                const int64_t o = (((int64_t)n * DH + dy) * DW + dx) * C + c4 * 4;
+                const float a[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) resize_store(a[e], o + e, n, C, c4 * 4 + e, dst, style, hi, lo);
+            }
+        }
+    }
+}
+
+// Any other channel count (the 3-channel raw image): one thread per (destination pixel, channel).
+__global__ void __launch_bounds__(256) resize_aa_scalar_kernel(const float* __restrict__ src, int N, int SH, int SW, int C, const int* __restrict__ src_box,
+                                                               float* __restrict__ dst, int DH, int DW, const int* __restrict__ dst_box,
+                                                               const float* __restrict__ style, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+    const int64_t total = (int64_t)N * DH * DW * C;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % C);
+        const int64_t pi = idx / C;
+        const int n = (int)(pi / ((int64_t)DH * DW)), dy = (int)((pi / DW) % DH), dx = (int)(pi % DW);
+        ResizeWin w;
+        if (!resize_window(src_box, dst_box, n, SH, SW, DH, DW, dy, dx, w)) continue;
+        const AxisTaps ay = aa_axis(dy - w.ty0, w.ih, w.oh), ax = aa_axis(dx - w.tx0, w.iw, w.ow);
+        float acc = 0.f;
+        for (int j = 0; j < ay.n; ++j) {
+            const float* row = src + (((int64_t)n * SH + w.sy0 + ay.lo + j) * SW + w.sx0 + ax.lo) * C + c;
+            float racc = 0.f;
+            for (int i = 0; i < ax.n; ++i) racc += aa_weight(ax, i) * __ldg(row + (int64_t)i * C);
+            acc += aa_weight(ay, j) * racc;
+        }
+        resize_store(acc, idx, n, C, c, dst, style, hi, lo);
     }
 }
 
@@ -456,8 +517,14 @@ extern "C" int n3d_resize_aa(const float* src, int N, int SH, int SW, int C, con
                              const int32_t* dst_box, const float* style, void* hi, void* lo, void* stream) {
     N3D_CHECK_ARG(src && (dst || hi) && N > 0 && C > 0, "n3d_resize_aa: bad args");
     N3D_CHECK_ARG(!hi || lo, "n3d_resize_aa: hi without lo");
-    resize_aa_kernel<<<grid_for((int64_t)N * DH * DW * 32, 256, 16), 256, 0, (cudaStream_t)stream>>>(src, N, SH, SW, C, src_box, dst, DH, DW, dst_box, style,
-                                                                                                  (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+    const bool wide = (C % 4 == 0) && C <= 128 && (32 % (C / 4) == 0) && ((uintptr_t)src % 16 == 0);
+    const int ppw = dst_box ? 8 : 4;      // paste mode: most pixels are outside the window, test 8 per warp step
+    if (wide)
+        resize_aa_kernel<<<grid_for((int64_t)N * DH * DW * 32 / ppw, 256, 16), 256, 0, (cudaStream_t)stream>>>(
+            src, N, SH, SW, C, src_box, dst, DH, DW, dst_box, style, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, ppw);
+    else
+        resize_aa_scalar_kernel<<<grid_for((int64_t)N * DH * DW * C, 256, 16), 256, 0, (cudaStream_t)stream>>>(
+            src, N, SH, SW, C, src_box, dst, DH, DW, dst_box, style, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
     N3D_CHECK_LAUNCH("n3d_resize_aa");
     return N3D_OK;
 }

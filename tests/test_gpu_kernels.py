@@ -39,7 +39,8 @@ def _join(hi, lo):
 # ------------------------------------------------------------------------------------------------ conv_gemm
 @pytest.mark.parametrize('N,Cin,Cout,res', [(1, 32, 32, 16), (2, 64, 128, 16), (8, 512, 512, 4), (2, 512, 512, 8), (1, 128, 96, 32),
                                            (1, 256, 3, 32), (2, 16, 16, 64), (1, 128, 256, 64), (3, 96, 64, 24), (1, 1024, 512, 8),
-                                           (1, 32, 256, 128)])
+                                           (1, 32, 256, 128),
+                                           (2, 32, 128, 280), (1, 64, 128, 400)])      # block_n 128, >= 8 waves: M=256 pair-tile mode
 def test_conv3x3_plain(K, N, Cin, Cout, res):
     g = _g(N * 1000 + Cin + Cout + res)
     x = torch.randn(N, Cin, res, res, generator=g)
@@ -114,7 +115,8 @@ def test_conv1x1_torgb_nchw_accumulate(K):
     assert range_rel_err(out.cpu(), ref) < 3e-5
 
 
-@pytest.mark.parametrize('N,Cin,Cout,res,nchw,with_out', [(2, 64, 128, 32, True, True), (1, 128, 256, 16, False, True), (2, 32, 128, 32, True, False)])
+@pytest.mark.parametrize('N,Cin,Cout,res,nchw,with_out', [(2, 64, 128, 32, True, True), (1, 128, 256, 16, False, True), (2, 32, 128, 32, True, False),
+                                                         (2, 32, 128, 280, True, False)])     # last: pair-tile mode
 def test_conv_fused_torgb(K, N, Cin, Cout, res, nchw, with_out):
     """ToRGBLayer (networks_stylegan2.py:353-357) folded into the producing conv's epilogue: img += clamp(W_rgb (y * s_rgb) + b_rgb),
     optionally with no other output of the conv at all (last super-resolution layer)."""
@@ -146,7 +148,7 @@ def test_conv_fused_torgb(K, N, Cin, Cout, res, nchw, with_out):
         assert range_rel_err(_join(o_hi, o_lo).permute(0, 3, 1, 2).cpu(), y * s_next[:, :, None, None]) < 5e-5
 
 
-@pytest.mark.parametrize('N,Cin,Cout,res', [(2, 64, 64, 8), (1, 512, 512, 4), (1, 32, 256, 32), (2, 128, 64, 16)])
+@pytest.mark.parametrize('N,Cin,Cout,res', [(2, 64, 64, 8), (1, 512, 512, 4), (1, 32, 256, 32), (2, 128, 64, 16), (2, 32, 128, 150)])
 def test_upconv_modulated(K, N, Cin, Cout, res):
     """4 transposed-conv parity GEMMs + FIR epilogue == the reference's up=2 modulated conv + bias_act (oracle)."""
     from oracle import ops as oo

@@ -49,6 +49,22 @@ def main(tag):
         us = timeit(lambda: K.fir_up_epilogue(raw, cout, d, b, nz, 2 ** 0.5, 0.2, 256.0, outs=outs))
         gb = raw.numel() * 4 + o_hi.numel() * 4
         print(f'fir_up  C={cout:4d} out {2 * res:3d}^2      {us:8.1f} us  {gb / us * 1e-3:6.0f} GB/s')
+    for cin, cout, res in [(128, 128, 512), (128, 128, 256), (256, 256, 128), (512, 512, 64)]:
+        x = torch.randn(N, res, res, cin, device=DEV, generator=g)
+        hi, lo = K.split_bf16(x)
+        del x
+        w = torch.randn(cout, cin, 3, 3, device=DEV, generator=g) / (cin * 9) ** 0.5
+        w_hi, w_lo = K.pack_conv_weight(w)
+        o_hi = torch.empty(N, res, res, cout, device=DEV, dtype=torch.bfloat16)
+        o_lo = torch.empty_like(o_hi)
+        d = torch.rand(N, cout, device=DEV) + 0.5
+        b = torch.randn(cout, device=DEV)
+        st = torch.randn(N, cout, device=DEV)
+        outs = [K.make_split_out(o_hi, o_lo, st, cout, 0)]
+        us = timeit(lambda: K.conv_gemm(hi, lo, w_hi, w_lo, K.taps_conv3x3(), N, res, res, dcoef=d, bias=b, gain=2 ** 0.5, slope=0.2, clamp=256.0, outs=outs))
+        fl = 2.0 * cin * cout * 9 * N * res * res
+        print(f'conv3x3 {cin:4d}->{cout:4d} @{res:3d}^2  {us:8.1f} us  {fl / us * 1e-6:6.1f} TF/s')
+        del hi, lo, o_hi, o_lo
     for c, res in [(128, 256), (256, 128), (512, 64)]:
         x = torch.randn(N, res, res, c, device=DEV, generator=g)
         sh = (res + 2) // 2
