@@ -59,7 +59,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100', '-i', str(self.idx)],
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '20', '-i', str(self.idx)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -68,9 +68,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(',')])
+            self.rows.append([time.perf_counter()] + [x.strip() for x in line.split(',')])
 
-    def stop(self):
+    def stop(self, window=None):
+        """Median SM clock / throttle reasons of the samples that arrived inside `window` = (t0, t1) perf_counter times of the
+        timed region; if nvidia-smi delivered none in there (the region is a few hundred ms), of all samples taken under the same
+        load (timed region + end-to-end loop), and says which."""
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         self.proc.terminate()
@@ -78,8 +81,14 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        rows, scope = self.rows, 'timed region + e2e loop (same load)'
+        if window is not None:
+            inside = [r for r in self.rows if window[0] <= r[0] <= window[1]]
+            if inside:
+                rows, scope = inside, 'timed region'
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
+            r = r[1:]
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
                 for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[4:8]):
@@ -88,7 +97,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': sorted(reasons),
-                'samples': len(sm)}
+                'samples': len(sm), 'window': scope}
 
 
 def _cpu_threads():
@@ -217,6 +226,7 @@ def run_ours(args):
             sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        t_begin = time.perf_counter()
         e0.record()
         for i in range(args.steps):
             step_device(i)
@@ -224,8 +234,8 @@ def run_ours(args):
             torch.cuda.current_stream(dev).wait_stream(side)
         e1.record()
         barrier()
+        t_end = time.perf_counter()
         dt = D.max_over_ranks(e0.elapsed_time(e1) / 1e3, dev)
-        clocks = sampler.stop() if sampler else None
 
         # ---- end to end through the public API: pinned host inputs -> synthesis -> images on the host
         host_out = torch.empty(B * world if rank == 0 else B, 3, 512, 512).pin_memory()
@@ -239,6 +249,7 @@ def run_ours(args):
         e3.record()
         barrier()
         dt_e2e = D.max_over_ranks(e2.elapsed_time(e3) / 1e3, dev)
+        clocks = sampler.stop((t_begin, t_end)) if sampler else None
 
         # ---- per-kernel device times (CUDA events around every launch of the two graded kernels), one extra step
         roof = roof_r = None

@@ -389,8 +389,49 @@ __global__ void __launch_bounds__(256) resize_aa_kernel(const float* __restrict_
             ResizeWin w;
             resize_window(src_box, dst_box, n, SH, SW, DH, DW, dy, dx, w);
             const AxisTaps ay = aa_axis(dy - w.ty0, w.ih, w.oh), ax = aa_axis(dx - w.tx0, w.iw, w.ow);
-            const float4* win = reinterpret_cast<const float4*>(src + (((int64_t)n * SH + w.sy0 + ay.lo) * SW + w.sx0 + ax.lo) * C) + c4;
             const int nt = ay.n * ax.n;
+            const float4* win0 = reinterpret_cast<const float4*>(src + (((int64_t)n * SH + w.sy0 + ay.lo) * SW + w.sx0 + ax.lo) * C);
+            const int64_t o = (((int64_t)n * DH + dy) * DW + dx) * C;
+            if (nt >= 64 && c4n <= 8) {
+                // Strong minification (the 256^2 -> ~40^2 mouth paste: ~200 taps): every lane is a tap lane and fetches all
+                // channels of its taps (independent 128-byte loads), then one butterfly reduction over the warp.
+                float4 acc[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int t = lane; t < nt; t += 32) {
+                    const int j = t / ax.n, i = t - j * ax.n;
+                    const float wt = aa_weight(ay, j) * aa_weight(ax, i);
+                    const float4* tp = win0 + ((int64_t)j * SW + i) * c4n;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        if (k < c4n) {
+                            const float4 v = __ldg(tp + k);
+                            acc[k].x = fmaf(wt, v.x, acc[k].x); acc[k].y = fmaf(wt, v.y, acc[k].y);
+                            acc[k].z = fmaf(wt, v.z, acc[k].z); acc[k].w = fmaf(wt, v.w, acc[k].w);
+                        }
+                    }
+                }
+                float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (k < c4n) {
+                        float4 a = acc[k];
+#pragma unroll
+                        for (int off = 16; off >= 1; off >>= 1) {
+                            a.x += __shfl_xor_sync(0xffffffffu, a.x, off); a.y += __shfl_xor_sync(0xffffffffu, a.y, off);
+                            a.z += __shfl_xor_sync(0xffffffffu, a.z, off); a.w += __shfl_xor_sync(0xffffffffu, a.w, off);
+                        }
+                        if (lane == k) mine = a;
+                    }
+                }
+                if (lane < c4n) {
+                    const float a[4] = {mine.x, mine.y, mine.z, mine.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) resize_store(a[e], o + lane * 4 + e, n, C, lane * 4 + e, dst, style, hi, lo);
+                }
+                continue;
+            }
+            const float4* win = win0 + c4;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
             for (int t = tl; t < nt; t += ntl) {
@@ -404,10 +445,9 @@ __global__ void __launch_bounds__(256) resize_aa_kernel(const float* __restrict_
                 acc.z += __shfl_xor_sync(0xffffffffu, acc.z, off); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, off);
             }
             if (tl == 0) {
-                const int64_t o = (((int64_t)n * DH + dy) * DW + dx) * C + c4 * 4;
                 const float a[4] = {acc.x, acc.y, acc.z, acc.w};
 #pragma unroll
-                for (int e = 0; e < 4; ++e) resize_store(a[e], o + e, n, C, c4 * 4 + e, dst, style, hi, lo);
+                for (int e = 0; e < 4; ++e) resize_store(a[e], o + c4 * 4 + e, n, C, c4 * 4 + e, dst, style, hi, lo);
             }
         }
     }
@@ -518,7 +558,7 @@ extern "C" int n3d_resize_aa(const float* src, int N, int SH, int SW, int C, con
     N3D_CHECK_ARG(src && (dst || hi) && N > 0 && C > 0, "n3d_resize_aa: bad args");
     N3D_CHECK_ARG(!hi || lo, "n3d_resize_aa: hi without lo");
     const bool wide = (C % 4 == 0) && C <= 128 && (32 % (C / 4) == 0) && ((uintptr_t)src % 16 == 0);
-    const int ppw = dst_box ? 8 : 4;      // paste mode: most pixels are outside the window, test 8 per warp step
+    const int ppw = 4;
     if (wide)
         resize_aa_kernel<<<grid_for((int64_t)N * DH * DW * 32 / ppw, 256, 16), 256, 0, (cudaStream_t)stream>>>(
             src, N, SH, SW, C, src_box, dst, DH, DW, dst_box, style, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, ppw);
