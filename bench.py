@@ -24,6 +24,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+WORKLOAD = 'FFHQ-512 generator forward (TriPlaneGenerator.synthesis): 64^2 neural render -> 512^2 SR, 48+48 depth samples, '
 METRIC = 'generator images/sec at 512^2 (64^2 neural render, 48+48 samples/ray)'
 UNIT = 'img/s'
 
@@ -133,7 +134,9 @@ def run_reference(args):
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-        'data': 'synthetic', 'config': {'workload': 'FFHQ-512 generator forward, 64^2 render, 48+48 spp, batch 1 per step (CPU)'},
+        'data': 'synthetic',
+        'config': {'workload': WORKLOAD + f'batch {args.batch} per GPU', 'global_batch': args.batch,
+                   'sample': 'each step = 1 image of that workload (bounded sample: the CPU path takes ~2 s per image), host cores only'},
         'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
 
@@ -285,8 +288,7 @@ def run_ours(args):
         'metric': METRIC, 'value': imgs / dt, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'bf16x3 (hi/lo split operands, fp32 accumulate) for convs; f32 elsewhere', 'data': 'synthetic',
-        'config': {'workload': 'FFHQ-512 generator forward (TriPlaneGenerator.synthesis): 64^2 neural render -> 512^2 SR, 48+48 depth samples, '
-                               f'batch {B} per GPU', 'global_batch': B * world, 'parallelism': f'batch-sharded x{world}, one gather of images',
+        'config': {'workload': WORKLOAD + f'batch {B} per GPU', 'global_batch': B * world, 'parallelism': f'batch-sharded x{world}, one gather of images',
                    'launch': 'eager' if args.no_graph else 'one CUDA graph replay per step',
                    'l2': 'no explicit flush: per-step working set (0.7 GB packed weights + >4 GB activations) >> 126 MB L2'},
         'clocks': clocks,

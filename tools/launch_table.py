@@ -1,4 +1,4 @@
-"""Aggregate an ncu launch list (--metrics gpu__time_duration.sum --csv) into a per-kernel table for one generator step.
+"""Aggregate an ncu launch list (--metrics gpu__time_duration.sum[,...] --csv) into a per-kernel table for one generator step.
 Usage: python tools/launch_table.py gpurun_out/launches.csv > profiles/rNN_launches_summary.txt"""
 import collections
 import csv
@@ -12,7 +12,9 @@ def main(path):
     r = csv.reader(lines)
     h = next(r)
     ix = {n: i for i, n in enumerate(h)}
-    rows = [(re.sub(r'<unnamed>::', '', row[ix['Kernel Name']]).split('(')[0], float(row[ix['Metric Value']]) / 1e3) for row in r]
+    unit = {'ns': 1e-3, 'nsecond': 1e-3, 'us': 1.0, 'usecond': 1.0, 'ms': 1e3, 'msecond': 1e3}
+    rows = [(re.sub(r'<unnamed>::|void ', '', row[ix['Kernel Name']]).split('(')[0], float(row[ix['Metric Value']].replace(',', '')) * unit.get(row[ix['Metric Unit']], 1e-3))
+            for row in r if row[ix['Metric Name']] == 'gpu__time_duration.sum']      # the list may carry further metrics (DRAM bytes) per launch
     starts = [i for i, (n, _) in enumerate(rows) if n == 'styles_kernel']
     if len(starts) >= 2:
         rows = rows[starts[0]:starts[1]]
