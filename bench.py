@@ -258,7 +258,8 @@ def run_ours(args):
         roof = roof_r = None
         if rank == 0:
             eng.prof = []
-            G.use_cuda_graph = False                         # events around every launch need the eager path
+            G.use_cuda_graph = False                         # events around every launch need the eager path ...
+            eng.concurrent = False                           # ... and one stream: a kernel sharing the SMs with another branch is not its own time
             G.synthesis(ws_d, c_d, v_d, noise_mode='const', seed=5)
             summ = eng.profile_summary()
             eng.prof = None

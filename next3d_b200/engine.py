@@ -12,6 +12,7 @@ Execution model:
 Reference call order: triplane_next3d.py:117-188.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -82,6 +83,8 @@ class Engine:
         self.eye_mask = mask.reshape(mask.shape[-2], mask.shape[-1]).to(self.device, torch.float32).contiguous()
         self._mm_init = torch.tensor([float('inf'), 0.0], device=self.device)
         self._graphs = {}
+        self._side = None                       # side streams of the concurrent branches (compute_planes)
+        self.concurrent = os.environ.get('N3D_CONCURRENT', '1') != '0'
 
     # ------------------------------------------------------------------------------------------ packing (one-time)
     def _add_mod(self, sd, name, cin, cout, k, up, widx, is_rgb=False, clamp=None, noise=True):
@@ -491,23 +494,42 @@ class Engine:
         K.styles(ws, self.aff_w, self.aff_b, self.row_widx, self.row_scale, s_ooff, self.row_cin, self._styles)
         K.demod(self._styles, self.wsq, self.d_woff, self.d_cin, d_soff, d_ooff, self.d_cout, self._dcoefs, N)
         self.launches += 2
-        # neural texture
+        # Three independent branches (triplane_next3d.py:137-170): (1) neural texture -> UV lookup -> mouth / blending UNets,
+        # (2) mesh rasterization + mouth box (needs only the vertices), (3) the static tri-plane backbone (needed only by the final
+        # blend).  (2) and (3) run on side streams: their latency-bound kernels (4^2..32^2 layers on a few dozen SMs, the flood
+        # fill, the rasterizer) fill SMs the main branch leaves idle and vice versa.  Captured as parallel graph branches.
+        main = torch.cuda.current_stream(dev)
+        if self.concurrent:
+            if self._side is None:
+                self._side = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+            s_rast, s_static = self._side
+            s_rast.wait_stream(main)
+            s_static.wait_stream(main)
+        else:
+            s_rast = s_static = main
+        with torch.cuda.stream(s_rast):
+            tv = self._f32(N, 4, verts.shape[1], 3)
+            K.transform_points(verts, self.rot, 10.0, True, tv)
+            tl = self._f32(N, 4, lms.shape[1], 3)
+            K.transform_points(lms, self.rot, 0.0, False, tl)
+            p2f = torch.empty(N * 4, P, P, dtype=torch.int32, device=dev)
+            bary = self._f32(N * 4, P, P, 3)
+            K.rasterize(tv.view(N * 4, -1, 3), self.faces, P, P, p2f, bary)
+            boxes = torch.empty(N, 4, dtype=torch.int32, device=dev)
+            lm2d = tl[:, 0, :, :2].contiguous()
+            K.mouth_box(lm2d, boxes)
+        with torch.cuda.stream(s_static):
+            static = self._backbone('backbone.synthesis', cfg.plane_ch * 3, noise_mode)             # [N,256,256,96]
         textures = self._backbone('texture_backbone.synthesis', cfg.plane_ch, noise_mode)          # [N,256,256,32]
-        # rasterize the 4 views, look up texture + eye mask, fill the mouth hole
-        tv = self._f32(N, 4, verts.shape[1], 3)
-        K.transform_points(verts, self.rot, 10.0, True, tv)
-        tl = self._f32(N, 4, lms.shape[1], 3)
-        K.transform_points(lms, self.rot, 0.0, False, tl)
-        p2f = torch.empty(N * 4, P, P, dtype=torch.int32, device=dev)
-        bary = self._f32(N * 4, P, P, 3)
-        K.rasterize(tv.view(N * 4, -1, 3), self.faces, P, P, p2f, bary)
+        if self.concurrent:
+            main.wait_stream(s_rast)
+            for t in (p2f, bary, boxes, lm2d):
+                t.record_stream(main)
+        # look up texture + eye mask at the rasterized UVs, fill the mouth hole
         tex_planes = self._f32(3, N, P, P, cfg.plane_ch)
         alpha = self._f32(3, N, P, P)
         K.uv_sample(p2f, bary, self.face_uv, textures, self.eye_mask, tex_planes, alpha)
         K.fill_mouth(alpha)
-        boxes = torch.empty(N, 4, dtype=torch.int32, device=dev)
-        lm2d = tl[:, 0, :, :2].contiguous()
-        K.mouth_box(lm2d, boxes)
         self.launches += 7                                                          # rasterize = setup pass + bin pass
         # mouth crop -> StyleUNet -> paste back -> neural blending
         front = tex_planes[0]
@@ -517,7 +539,9 @@ class Engine:
         stitched = front.clone()
         K.resize_aa(mouth, stitched, dst_box=boxes)
         blended = self._styleunet('neural_blending.synthesis', stitched, 256, 32, 256, noise_mode)
-        static = self._backbone('backbone.synthesis', cfg.plane_ch * 3, noise_mode)                 # [N,256,256,96]
+        if self.concurrent:
+            main.wait_stream(s_static)
+            static.record_stream(main)
         planes = self._f32(N, 3, P, P, cfg.plane_ch)
         K.blend_planes(blended, tex_planes, alpha, static, planes)
         self.launches += 3

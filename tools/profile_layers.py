@@ -15,6 +15,7 @@ eng = G._get_engine()
 for _ in range(3):
     G.synthesis(ws, c.cuda(), v.cuda(), noise_mode='const', seed=1)
 eng.prof = []
+eng.concurrent = False          # per-kernel times: no concurrent branches
 G.synthesis(ws, c.cuda(), v.cuda(), noise_mode='const', seed=1)
 torch.cuda.synchronize()
 rows = [(info, e0.elapsed_time(e1) * 1e3, fl) for kind, e0, e1, fl, info in eng.prof if kind == 'conv_gemm']
