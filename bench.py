@@ -202,7 +202,14 @@ def run_ours(args):
                 D.gather_images(out['image'], dst=0)
         return out
 
+    copy_s = torch.cuda.Stream(dev)
+    stage, drained = [None, None], [None, None]
+
     def step_e2e(i, host_out):
+        """One end-to-end step the way a serving loop would run it: H2D of the inputs, synthesis, and the D2H of the images on a
+        copy stream from a ping-pong staging buffer, so that the 25 MB read-back of step i overlaps the compute of step i+1
+        (the graph's static output buffer is free again after an 8 us device copy)."""
+        main = torch.cuda.current_stream(dev)
         w = ws_host.to(dev, non_blocking=True)
         c = c_host.to(dev, non_blocking=True)
         vv = v_host.to(dev, non_blocking=True)
@@ -211,7 +218,17 @@ def run_ours(args):
         if world > 1:
             img = D.gather_images(img, dst=0)
         if img is not None:
-            host_out[: img.shape[0]].copy_(img, non_blocking=True)
+            k = i & 1
+            if drained[k] is not None:
+                main.wait_event(drained[k])                 # the D2H of step i-2 has left this staging buffer
+            if stage[k] is None:
+                stage[k] = torch.empty_like(img)
+            stage[k].copy_(img)
+            copy_s.wait_stream(main)
+            with torch.cuda.stream(copy_s):
+                host_out[: img.shape[0]].copy_(stage[k], non_blocking=True)
+                drained[k] = torch.cuda.Event()
+                drained[k].record(copy_s)
         return out
 
     def barrier():
@@ -249,6 +266,7 @@ def run_ours(args):
         e2.record()
         for i in range(args.steps):
             step_e2e(i, host_out)
+        torch.cuda.current_stream(dev).wait_stream(copy_s)   # the last read-back is inside the timed region
         e3.record()
         barrier()
         dt_e2e = D.max_over_ranks(e2.elapsed_time(e3) / 1e3, dev)

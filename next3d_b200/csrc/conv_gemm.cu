@@ -27,6 +27,7 @@ constexpr int kBlockM = 128;
 // 32 bf16 (64-byte rows, SWIZZLE_64B) so that no TMA box hangs over the channel extent.
 constexpr int kThreads = 384;                 // warps 0-3: producer / MMA / TMEM alloc / spare; 4-7 and 8-11: two epilogue groups
 constexpr int kMaxBlockN = 256;
+constexpr int kMinTiles = 64;                 // see the block_n choice in launch_conv
 constexpr int kStageArrays = 8;               // dcoef | bias | style0 | style1 | up to 4 modulated ToRGB weight rows
 
 struct KParams {
@@ -464,8 +465,10 @@ int launch_conv(const N3DConvGemm* p, int nsub, const SubSpec* specs, void* stre
         K.sub[i].tiles_x = n3d_div_up(specs[i].MW, K.TW); K.sub[i].tiles_y = n3d_div_up(specs[i].MH, K.TH);
         tiles_m += K.sub[i].tiles_x * K.sub[i].tiles_y * K.tiles_i;
     }
-    // block_n: the largest legal UMMA N (M=128 needs N % 16 == 0) not exceeding Cout, shrunk while the launch would
-    // not fill one wave of the 148 SMs.
+    // block_n: the largest legal UMMA N (M=128 needs N % 16 == 0) not exceeding Cout, halved while the launch has fewer than
+    // kMinTiles tiles.  Narrow tiles re-fetch the activation tile once per n-tile, so filling all 148 SMs with block_n = 32 tiles is
+    // slower than 64 SMs with block_n = 128 (512->512 @16^2, batch 8: 107 -> 60 us; 1024->512 @16^2: 206 -> 110 us; thresholds 64
+    // and 96 measured equal, 32 and 148 worse; tools/bench_layers.py).
     const int cout16 = ((p->Cout + 15) / 16) * 16;
     int bn = 16;
     {
@@ -476,7 +479,7 @@ int launch_conv(const N3DConvGemm* p, int nsub, const SubSpec* specs, void* stre
             bn = cands[i];
             break;
         }
-        while (bn > 32 && tiles_m * n3d_div_up(p->Cout, bn) < 148) bn = (bn == 96) ? 32 : bn / 2;
+        while (bn > 32 && tiles_m * n3d_div_up(p->Cout, bn) < kMinTiles) bn = (bn == 96) ? 32 : bn / 2;
         if (p->rgb.out) {                                   // fused ToRGB needs every output channel of a pixel in one tile
             N3D_CHECK_ARG(cout16 <= 256 && cout16 % 16 == 0, "n3d_conv_gemm: fused ToRGB needs Cout <= 256");
             N3D_CHECK_ARG(p->rgb.channels >= 1 && p->rgb.channels <= 4 && p->rgb.weight && p->rgb.style && p->rgb.bias, "n3d_conv_gemm: bad fused ToRGB descriptor");

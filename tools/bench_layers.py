@@ -49,7 +49,8 @@ def main(tag):
         us = timeit(lambda: K.fir_up_epilogue(raw, cout, d, b, nz, 2 ** 0.5, 0.2, 256.0, outs=outs))
         gb = raw.numel() * 4 + o_hi.numel() * 4
         print(f'fir_up  C={cout:4d} out {2 * res:3d}^2      {us:8.1f} us  {gb / us * 1e-3:6.0f} GB/s')
-    for cin, cout, res in [(128, 128, 512), (128, 128, 256), (256, 256, 128), (512, 512, 64)]:
+    for cin, cout, res in [(128, 128, 512), (128, 128, 256), (256, 256, 128), (512, 512, 64), (512, 512, 32), (512, 512, 16), (512, 512, 8), (512, 512, 4),
+                           (1024, 512, 32), (1024, 512, 16), (1024, 512, 8)]:
         x = torch.randn(N, res, res, cin, device=DEV, generator=g)
         hi, lo = K.split_bf16(x)
         del x
