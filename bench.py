@@ -29,6 +29,25 @@ METRIC = 'generator images/sec at 512^2 (64^2 neural render, 48+48 samples/ray)'
 UNIT = 'img/s'
 
 
+_JSON_OUT = None
+
+
+def _guard_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print to file descriptor 1 behind Python's back (NCCL's version banner,
+    for one): keep a private duplicate of the real stdout for the JSON line and point fd 1 at stderr for everything else."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), 'w')
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + '\n')
+    out.flush()
+
+
 def _traffic(kernel):
     """Measured DRAM bytes per launch of `kernel` (dram__bytes_read + dram__bytes_write, ncu capture of one forward at the bench
     batch size, summarised by tools/dram_table.py into profiles/): (bytes, source) or (None, None)."""
@@ -131,14 +150,14 @@ def run_reference(args):
         dt = time.perf_counter() - t0
     val = args.steps / dt
     sample = f'{args.steps} steps x 1 image (batch 1) of the same generator/config, fp32 torch CPU ops, {cores} threads (of {os.cpu_count()} host cores; more threads are slower, see bench.py::_cpu_threads)'
-    print(json.dumps({
+    _emit({
         'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic',
         'config': {'workload': WORKLOAD + f'batch {args.batch} per GPU', 'global_batch': args.batch,
                    'sample': 'each step = 1 image of that workload (bounded sample: the CPU path takes ~2 s per image), host cores only'},
         'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
-        'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+        'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}})
 
 
 def cpu_baseline_sample():
@@ -318,7 +337,7 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         line['cpu_baseline'] = cpu_baseline_sample()
-    print(json.dumps(line))
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -333,6 +352,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='launch kernels eagerly instead of replaying the captured CUDA graph')
     args = ap.parse_args()
+    _guard_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     if args.impl == 'reference':
         run_reference(args)

@@ -16,8 +16,9 @@ def init_from_env(backend=None):
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     if world > 1 and not dist.is_initialized():
-        if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', ''):
-            os.environ['NCCL_DEBUG'] = 'WARN'      # keep rank 0's stdout to the single JSON line (NCCL prints its banner to stdout)
+        # NCCL writes its debug output (the version banner included, at any NCCL_DEBUG level) to STDOUT unless told otherwise:
+        # send it to stderr so that a caller's stdout stays machine-readable (bench.py prints one JSON line)
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         backend = backend or ('nccl' if torch.cuda.is_available() else 'gloo')
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         if backend == 'nccl':
