@@ -254,6 +254,20 @@ int n3d_sample_points(const float* planes, int N, int PH, int PW, const float* c
                       const float* w0, const float* b0, const float* w1, const float* b1, float* sigma, float* rgb,
                       void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Host-side input parsers (no device work): what the inference scripts do per frame in Python.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* Vertex positions of a Wavefront .obj text (gen_samples_next3d.py:165-174: every line with line[:2] == "v ", tokens after the
+ * first converted with float(), all numbers flattened and reshaped to (-1, 3), then .float()).  text need not be NUL-terminated.
+ * Writes up to max_vertices * 3 floats; *n_vertices receives the count (also when it exceeds max_vertices -> INVALID_ARG, so a
+ * caller can size the buffer with max_vertices = 0 first). */
+int n3d_parse_obj_vertices(const char* text, int64_t len, float* xyz, int64_t max_vertices, int64_t* n_vertices);
+
+/* Whitespace-separated table of numbers with '#' comments, the subset of np.loadtxt the scripts use for *_kpt2d.txt
+ * (gen_samples_next3d.py:176-177): float64 parse, float32 store; every non-empty row must have *n_cols columns. */
+int n3d_parse_float_table(const char* text, int64_t len, float* values, int64_t max_values, int64_t* n_values, int64_t* n_cols);
+
 #ifdef __cplusplus
 }
 #endif

@@ -73,6 +73,8 @@ _SIGNATURES = {
     'n3d_conv_transposed_gemm': ([C.POINTER(ConvGemm), P], C.c_int),
     'n3d_modulate_split': ([P, I64, C.c_int, C.c_int, P, P, P, C.c_int, C.c_int, P], C.c_int),
     'n3d_fir_up_epilogue': ([P, C.c_int, C.c_int, C.c_int, C.c_int, P, P, P, I64, F32, F32, F32, C.POINTER(SplitOut), P, C.c_int, C.c_int, P], C.c_int),
+    'n3d_parse_obj_vertices': ([C.c_char_p, I64, P, I64, C.POINTER(I64)], C.c_int),
+    'n3d_parse_float_table': ([C.c_char_p, I64, P, I64, C.POINTER(I64), C.POINTER(I64)], C.c_int),
     'n3d_fir_down_split': ([P, C.c_int, C.c_int, C.c_int, C.c_int, P, P, P], C.c_int),
     'n3d_upsample2d_nhwc': ([P, C.c_int, C.c_int, C.c_int, C.c_int, P, C.c_int, P], C.c_int),
     'n3d_downsample2d_nhwc': ([P, C.c_int, C.c_int, C.c_int, C.c_int, P, P], C.c_int),
