@@ -22,7 +22,7 @@ def look_at_pose(horizontal, vertical, lookat, radius):
     origin = torch.stack([radius * torch.sin(phi) * torch.cos(math.pi - theta),
                           radius * torch.cos(phi),
                           radius * torch.sin(phi) * torch.sin(math.pi - theta)])
-    fwd = _normalize(torch.as_tensor(lookat, dtype=torch.float32) - origin)
+    fwd = _normalize(_normalize(torch.as_tensor(lookat, dtype=torch.float32) - origin))   # normalised twice, like the reference (:85 and :124)
     up = torch.tensor([0., 1., 0.])
     right = -_normalize(torch.linalg.cross(up, fwd))
     up = _normalize(torch.linalg.cross(fwd, right))

@@ -1,0 +1,102 @@
+"""Batched frame drivers: the per-frame Python loops of `gen_videos_next3d.py:128-171` and
+`reenact_avatar_next3d.py:125-167` restated as (1) a frame schedule computed up front -- orbit cameras, interpolated latents --
+and (2) a loop over BATCHES of frames through `TriPlaneGenerator.synthesis` (CUDA-graph replay), with the uint8 conversion on
+the device and an asynchronous read-back, so that nothing but the generator sits on the critical path.
+
+Everything here is host logic around the hot path; the per-frame values (camera matrices, interpolated ws, uint8 pixels) are the
+reference's, checked in tests/test_drivers_cpu.py against the reference's own code.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import camera
+
+FOCAL_FFHQ = 4.2647            # gen_videos_next3d.py:97,139
+
+
+def orbit_camera_params(num_frames, lookat, radius, yaw_range=0.35, pitch_range=0.25, focal=FOCAL_FFHQ):
+    """-> c [num_frames, 25] float32: the camera sweep of gen_videos_next3d.py:128-140 (note the script's 3.14 literals)."""
+    intr = torch.tensor([[focal, 0, 0.5], [0, focal, 0.5], [0, 0, 1]], dtype=torch.float32)
+    half = num_frames // 2
+    out = []
+    for f in range(num_frames):
+        pose = camera.look_at_pose(3.14 / 2 + yaw_range * np.sin(2 * 3.14 * f / half),
+                                   3.14 / 2 - 0.05 + pitch_range * np.cos(2 * 3.14 * f / half), lookat, radius)
+        out.append(torch.cat([pose.reshape(16), intr.reshape(9)]))
+    return torch.stack(out)
+
+
+def interpolate_ws(ws_keyframes, w_frames, wraps=2, kind='cubic'):
+    """ws_keyframes [K, L, D] (one grid cell of gen_videos_next3d.py:106-117) -> [K * w_frames, L, D]: the latents of every
+    frame, `interp(frame_idx / w_frames)` for frame_idx = 0 .. K*w_frames-1 (:143-144), evaluated in one call."""
+    import scipy.interpolate
+    K = ws_keyframes.shape[0]
+    x = np.arange(-K * wraps, K * (wraps + 1))
+    y = np.tile(ws_keyframes.detach().cpu().numpy(), [wraps * 2 + 1, 1, 1])
+    interp = scipy.interpolate.interp1d(x, y, kind=kind, axis=0)
+    return torch.from_numpy(interp(np.arange(K * w_frames) / w_frames))
+
+
+def to_uint8_hwc(img):
+    """[N,3,H,W] float in [-1,1] -> [N,H,W,3] uint8, the arithmetic of layout_grid (gen_videos_next3d.py:40-46) for a 1x1 grid."""
+    return (img * 127.5 + 128).clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+
+
+def render_frames(G, ws_frames, cams, verts, batch=8, image_mode='image', noise_mode='const', device=None):
+    """Yield one uint8 HWC numpy frame per (ws, camera, mesh) triple, in order, rendering `batch` frames per synthesis call.
+
+    ws_frames [F, L, D], cams [F, 25], verts: [F, V, 3] / [1, V, 3] (static mesh) tensors, or an iterable of per-frame [1, V, 3]
+    tensors (e.g. inputs.FramePrefetcher).  The last, partial batch is padded by repeating its final frame (one graph shape) and
+    the padding is dropped.  The device->host copy of batch i overlaps the synthesis of batch i+1."""
+    device = device or next(G.parameters()).device
+    F = ws_frames.shape[0]
+    cuda = torch.device(device).type == 'cuda'
+    vit = None
+    if not torch.is_tensor(verts):
+        vit = iter(verts)
+    copy_s = torch.cuda.Stream(device) if cuda else None
+    pending = None                                               # (host tensor, event, valid count) of the previous batch
+
+    def drain(p):
+        host, ev, n = p
+        if ev is not None:
+            ev.synchronize()
+        for k in range(n):
+            yield host[k].numpy()
+
+    for b0 in range(0, F, batch):
+        n = min(batch, F - b0)
+        idx = list(range(b0, b0 + n)) + [b0 + n - 1] * (batch - n)
+        w = ws_frames[idx].to(device, torch.float32, non_blocking=True)
+        c = cams[idx].to(device, torch.float32, non_blocking=True)
+        if vit is not None:
+            vs = [next(vit) for _ in range(n)]
+            v = torch.cat(vs + [vs[-1]] * (batch - n), 0).to(device, torch.float32, non_blocking=True)
+        elif verts.shape[0] == 1:
+            v = verts.to(device, torch.float32).expand(batch, -1, -1)
+        else:
+            v = verts[idx].to(device, torch.float32, non_blocking=True)
+        img = G.synthesis(w, c, v, noise_mode=noise_mode)[image_mode]
+        if image_mode == 'image_depth':                          # gen_videos_next3d.py:160-162, per frame
+            img = -img
+            lo, hi = img.amin(dim=(1, 2, 3), keepdim=True), img.amax(dim=(1, 2, 3), keepdim=True)
+            img = (img - lo) / (hi - lo) * 2 - 1
+            img = img.expand(-1, 3, -1, -1) if img.shape[1] == 1 else img
+        u8 = to_uint8_hwc(img)                                   # fresh tensor: the generator's static output buffer is free again
+        if cuda:
+            host = torch.empty(u8.shape, dtype=torch.uint8).pin_memory()
+            copy_s.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(copy_s):
+                host.copy_(u8, non_blocking=True)
+                u8.record_stream(copy_s)
+                ev = torch.cuda.Event()
+                ev.record(copy_s)
+        else:
+            host, ev = u8, None
+        if pending is not None:
+            yield from drain(pending)
+        pending = (host, ev, n)
+    if pending is not None:
+        yield from drain(pending)

@@ -1,0 +1,90 @@
+"""Row f1 of SURVEY.md section 8 (batched frame drivers): the frame schedule and the batching logic against the reference's own
+per-frame code (gen_videos_next3d.py:96-171, camera_utils.py:68-86).  CPU only; the generator is a stub here, the real one is
+covered by tests/test_gpu_generator.py (batch invariance)."""
+import math
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from next3d_b200 import camera, drivers
+
+REF = '/root/reference'
+needs_ref = pytest.mark.skipif(not os.path.exists(os.path.join(REF, 'camera_utils.py')), reason='reference tree not present (GPU box)')
+
+
+@needs_ref
+def test_cameras_match_reference_sampler():
+    sys.path.insert(0, REF)
+    try:
+        import camera_utils
+    finally:
+        sys.path.remove(REF)
+    lookat = torch.tensor([0, 0, 0.2])
+    for h, v in [(math.pi / 2, math.pi / 2), (math.pi / 2 + 0.4, math.pi / 2 - 0.2), (0.3, 1e-7), (3.0, 3.2)]:
+        ref = camera_utils.LookAtPoseSampler.sample(h, v, lookat, radius=2.7)[0]
+        assert torch.equal(camera.look_at_pose(h, v, lookat, 2.7), ref)
+    assert torch.equal(camera.fov_to_intrinsics(18.837), camera_utils.FOV_to_intrinsics(18.837))
+    # the orbit of gen_videos_next3d.py:128-140, frame by frame
+    F = 24
+    c = drivers.orbit_camera_params(F, lookat, 2.7)
+    intr = torch.tensor([[4.2647, 0, 0.5], [0, 4.2647, 0.5], [0, 0, 1]])
+    for f in range(F):
+        pose = camera_utils.LookAtPoseSampler.sample(3.14 / 2 + 0.35 * np.sin(2 * 3.14 * f / (F // 2)),
+                                                      3.14 / 2 - 0.05 + 0.25 * np.cos(2 * 3.14 * f / (F // 2)), lookat, radius=2.7)
+        assert torch.equal(c[f], torch.cat([pose.reshape(-1, 16), intr.reshape(-1, 9)], 1)[0])
+
+
+def test_interpolated_latents_match_per_frame_calls():
+    import scipy.interpolate
+    g = torch.Generator().manual_seed(0)
+    K, w_frames, wraps = 3, 5, 2
+    ws = torch.randn(K, 28, 16, generator=g)
+    got = drivers.interpolate_ws(ws, w_frames, wraps)
+    x = np.arange(-K * wraps, K * (wraps + 1))                            # gen_videos_next3d.py:112-114
+    interp = scipy.interpolate.interp1d(x, np.tile(ws.numpy(), [wraps * 2 + 1, 1, 1]), kind='cubic', axis=0)
+    for f in range(K * w_frames):
+        assert np.array_equal(got[f].numpy(), interp(f / w_frames))      # :143-144
+    assert np.allclose(got[::w_frames].numpy(), ws.numpy(), atol=1e-6)    # passes through the key frames
+
+
+def test_uint8_conversion_is_layout_grid():
+    g = torch.Generator().manual_seed(1)
+    img = torch.randn(2, 3, 8, 8, generator=g) * 1.5
+    ref = (img * 127.5 + 128).clamp(0, 255).to(torch.uint8)               # gen_videos_next3d.py:41, then :42-46 with a 1x1 grid
+    for k in range(2):
+        r = ref[k:k + 1].reshape(1, 1, 3, 8, 8).permute(2, 0, 3, 1, 4).reshape(3, 8, 8).permute(1, 2, 0)
+        assert torch.equal(drivers.to_uint8_hwc(img)[k], r)
+
+
+class _StubG(torch.nn.Module):
+    """Deterministic stand-in with the generator's call signature: pixel = f(ws, c, v) per sample, independent of the batch."""
+    def __init__(self):
+        super().__init__()
+        self.p = torch.nn.Parameter(torch.zeros(1))
+        self.calls = []
+
+    def synthesis(self, ws, c, v, noise_mode='const'):
+        self.calls.append(ws.shape[0])
+        s = ws.mean(dim=(1, 2)) + c.mean(dim=1) + v.mean(dim=(1, 2))
+        img = torch.tanh(s)[:, None, None, None] * torch.linspace(-1, 1, 48).reshape(1, 3, 4, 4)
+        return {'image': img, 'image_depth': s[:, None, None, None].expand(-1, 1, 4, 4) + torch.arange(16.).reshape(1, 1, 4, 4)}
+
+
+@pytest.mark.parametrize('F,batch,mesh', [(10, 4, 'static'), (8, 8, 'per_frame'), (5, 3, 'iter'), (1, 8, 'static')])
+def test_batched_frames_equal_per_frame_loop(F, batch, mesh):
+    g = torch.Generator().manual_seed(2)
+    ws, cams = torch.randn(F, 28, 16, generator=g), torch.randn(F, 25, generator=g)
+    vf = torch.randn(F, 7, 3, generator=g)
+    G = _StubG()
+    verts = {'static': vf[:1], 'per_frame': vf, 'iter': (vf[i:i + 1] for i in range(F))}[mesh]
+    got = list(drivers.render_frames(G, ws, cams, verts, batch=batch, device='cpu'))
+    assert len(got) == F and all(n == batch for n in G.calls) and len(G.calls) == -(-F // batch)
+    for f in range(F):
+        v = vf[:1] if mesh == 'static' else vf[f:f + 1]
+        ref = drivers.to_uint8_hwc(_StubG().synthesis(ws[f:f + 1], cams[f:f + 1], v)['image'])[0].numpy()
+        assert np.array_equal(got[f], ref)
+    depth = list(drivers.render_frames(_StubG(), ws, cams, vf[:1], batch=batch, image_mode='image_depth', device='cpu'))
+    assert len(depth) == F and depth[0].shape == (4, 4, 3) and depth[0].max() == 255
