@@ -44,12 +44,13 @@ def to_uint8_hwc(img):
     return (img * 127.5 + 128).clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
 
 
-def render_frames(G, ws_frames, cams, verts, batch=8, image_mode='image', noise_mode='const', device=None):
+def render_frames(G, ws_frames, cams, verts, batch=8, image_mode='image', noise_mode='const', device=None, seed=None):
     """Yield one uint8 HWC numpy frame per (ws, camera, mesh) triple, in order, rendering `batch` frames per synthesis call.
 
     ws_frames [F, L, D], cams [F, 25], verts: [F, V, 3] / [1, V, 3] (static mesh) tensors, or an iterable of per-frame [1, V, 3]
     tensors (e.g. inputs.FramePrefetcher).  The last, partial batch is padded by repeating its final frame (one graph shape) and
-    the padding is dropped.  The device->host copy of batch i overlaps the synthesis of batch i+1."""
+    the padding is dropped.  The device->host copy of batch i overlaps the synthesis of batch i+1.  `seed`: base seed of the ray
+    sampler's RNG (batch k uses seed + k); None = a fresh random seed per call, like the reference's torch.rand."""
     device = device or next(G.parameters()).device
     F = ws_frames.shape[0]
     cuda = torch.device(device).type == 'cuda'
@@ -78,7 +79,8 @@ def render_frames(G, ws_frames, cams, verts, batch=8, image_mode='image', noise_
             v = verts.to(device, torch.float32).expand(batch, -1, -1)
         else:
             v = verts[idx].to(device, torch.float32, non_blocking=True)
-        img = G.synthesis(w, c, v, noise_mode=noise_mode)[image_mode]
+        kw = {} if seed is None else {'seed': int(seed) + b0 // batch}
+        img = G.synthesis(w, c, v, noise_mode=noise_mode, **kw)[image_mode]
         if image_mode == 'image_depth':                          # gen_videos_next3d.py:160-162, per frame
             img = -img
             lo, hi = img.amin(dim=(1, 2, 3), keepdim=True), img.amax(dim=(1, 2, 3), keepdim=True)

@@ -66,7 +66,7 @@ class _StubG(torch.nn.Module):
         self.p = torch.nn.Parameter(torch.zeros(1))
         self.calls = []
 
-    def synthesis(self, ws, c, v, noise_mode='const'):
+    def synthesis(self, ws, c, v, noise_mode='const', seed=None):
         self.calls.append(ws.shape[0])
         s = ws.mean(dim=(1, 2)) + c.mean(dim=1) + v.mean(dim=(1, 2))
         img = torch.tanh(s)[:, None, None, None] * torch.linspace(-1, 1, 48).reshape(1, 3, 4, 4)
