@@ -102,3 +102,55 @@ def render_frames(G, ws_frames, cams, verts, batch=8, image_mode='image', noise_
         pending = (host, ev, n)
     if pending is not None:
         yield from drain(pending)
+
+
+# ------------------------------------------------------------------------------------------------ shape extraction (row f2)
+def create_samples(N, cube_length, head=0, count=None, device='cpu'):
+    """Voxel-grid query points [1, count, 3] of `create_samples` (gen_samples_next3d.py:80-102) for the flat indices
+    head .. head+count-1, computed with the reference's own float32 operations (including its float -- not floor -- division,
+    which shears the y / x columns by idx / N, and the float32 rounding of indices above 2^24), so that any chunk is bit-identical
+    to the corresponding slice of the reference's full N^3 tensor without materialising it (201 MB at N = 256, 1.6 GB at 512)."""
+    count = N ** 3 - head if count is None else count
+    voxel_origin = np.array([0, 0, 0]) - cube_length / 2
+    voxel_size = cube_length / (N - 1)
+    idx = torch.arange(head, head + count, dtype=torch.int64, device=device)
+    s = torch.zeros(count, 3, device=device)
+    s[:, 2] = idx % N
+    s[:, 1] = (idx.float() / N) % N
+    s[:, 0] = ((idx.float() / N) / N) % N
+    s[:, 0] = (s[:, 0] * voxel_size) + voxel_origin[2]
+    s[:, 1] = (s[:, 1] * voxel_size) + voxel_origin[1]
+    s[:, 2] = (s[:, 2] * voxel_size) + voxel_origin[0]
+    return s.unsqueeze(0)
+
+
+def trim_sigma_grid(sigmas, shape_res, pad_value=-1000.0):
+    """flip + border trim of gen_samples_next3d.py:226-238 on a [R,R,R] tensor (device or host)."""
+    sigmas = torch.flip(sigmas, dims=[0])
+    pad = int(30 * shape_res / 256)
+    for d in range(3):
+        sl = [slice(None)] * 3
+        sl[d] = slice(0, pad)
+        sigmas[tuple(sl)] = pad_value
+        sl[d] = slice(shape_res - pad, shape_res)
+        sigmas[tuple(sl)] = pad_value
+    return sigmas
+
+
+def extract_sigma_grid(G, ws, v, shape_res=512, max_batch=1000000, noise_mode='const'):
+    """Density grid for marching cubes (gen_samples_next3d.py:208-238) -> float32 numpy [R,R,R], flipped and trimmed like the
+    script's.  The tri-planes are computed ONCE (the script's G.sample re-runs the three backbones for every 1M-point chunk: 17
+    times at 256^3, 135 times at 512^3), the query points are generated on the device chunk by chunk and only sigma is decoded."""
+    from . import kernels as K
+    eng = G._get_engine()
+    eng.rk = G.rendering_kwargs
+    planes = eng.compute_planes(ws, v, noise_mode)
+    dev = planes.device
+    total = shape_res ** 3
+    sigmas = torch.empty(total, device=dev)
+    box = G.rendering_kwargs['box_warp']
+    for head in range(0, total, max_batch):
+        n = min(max_batch, total - head)
+        coords = create_samples(shape_res, box * 1, head, n, device=dev)
+        K.sample_points(planes[:1], coords.contiguous(), box, eng.dec, sigmas[head:head + n].view(1, n), None)
+    return trim_sigma_grid(sigmas.view(shape_res, shape_res, shape_res), shape_res).cpu().numpy()

@@ -88,3 +88,48 @@ def test_batched_frames_equal_per_frame_loop(F, batch, mesh):
         assert np.array_equal(got[f], ref)
     depth = list(drivers.render_frames(_StubG(), ws, cams, vf[:1], batch=batch, image_mode='image_depth', device='cpu'))
     assert len(depth) == F and depth[0].shape == (4, 4, 3) and depth[0].max() == 255
+
+
+# ------------------------------------------------------------------------------------------------ row f2: shape extraction
+def ref_create_samples(N=256, voxel_origin=[0, 0, 0], cube_length=2.0):
+    """gen_samples_next3d.py:80-102, verbatim"""
+    voxel_origin = np.array(voxel_origin) - cube_length / 2
+    voxel_size = cube_length / (N - 1)
+    overall_index = torch.arange(0, N ** 3, 1, out=torch.LongTensor())
+    samples = torch.zeros(N ** 3, 3)
+    samples[:, 2] = overall_index % N
+    samples[:, 1] = (overall_index.float() / N) % N
+    samples[:, 0] = ((overall_index.float() / N) / N) % N
+    samples[:, 0] = (samples[:, 0] * voxel_size) + voxel_origin[2]
+    samples[:, 1] = (samples[:, 1] * voxel_size) + voxel_origin[1]
+    samples[:, 2] = (samples[:, 2] * voxel_size) + voxel_origin[0]
+    return samples.unsqueeze(0), voxel_origin, voxel_size
+
+
+@pytest.mark.parametrize('N', [17, 64])
+def test_chunked_samples_are_slices_of_the_reference_grid(N):
+    ref = ref_create_samples(N, cube_length=1.0)[0]
+    assert torch.equal(drivers.create_samples(N, 1.0), ref)
+    for head, n in [(0, 1000), (N ** 3 - 777, 777), (12345 % N ** 3, 2048)]:
+        n = min(n, N ** 3 - head)
+        assert torch.equal(drivers.create_samples(N, 1.0, head, n), ref[:, head:head + n])
+
+
+def test_large_index_rounding_like_the_reference():
+    """Indices above 2^24 are rounded by .float() in the reference; the chunked generator must reproduce that, not fix it."""
+    N, head, n = 512, 2 ** 26 + 12345, 4096
+    idx = torch.arange(head, head + n, dtype=torch.int64)
+    y = (idx.float() / N) % N
+    got = drivers.create_samples(N, 1.0, head, n)[0]
+    assert torch.equal(got[:, 1], y * (1.0 / (N - 1)) + (-0.5))
+    assert (idx.float().long() != idx).any()                              # the rounding really happens in this range
+
+
+def test_trim_matches_script():
+    R = 64
+    g = torch.Generator().manual_seed(3)
+    sig = torch.randn(R, R, R, generator=g)
+    ref = np.flip(sig.numpy().copy(), 0).copy()                           # gen_samples_next3d.py:226-238
+    pad = int(30 * R / 256)
+    ref[:pad] = -1000; ref[-pad:] = -1000; ref[:, :pad] = -1000; ref[:, -pad:] = -1000; ref[:, :, :pad] = -1000; ref[:, :, -pad:] = -1000
+    assert np.array_equal(drivers.trim_sigma_grid(sig.clone(), R).numpy(), ref)
