@@ -50,13 +50,14 @@ def test_interpolated_latents_match_per_frame_calls():
     assert np.allclose(got[::w_frames].numpy(), ws.numpy(), atol=1e-6)    # passes through the key frames
 
 
+@needs_ref
 def test_uint8_conversion_is_layout_grid():
+    layout_grid = _reference_scripts()[1].layout_grid                      # gen_videos_next3d.py:35-49
     g = torch.Generator().manual_seed(1)
     img = torch.randn(2, 3, 8, 8, generator=g) * 1.5
-    ref = (img * 127.5 + 128).clamp(0, 255).to(torch.uint8)               # gen_videos_next3d.py:41, then :42-46 with a 1x1 grid
+    got = drivers.to_uint8_hwc(img)
     for k in range(2):
-        r = ref[k:k + 1].reshape(1, 1, 3, 8, 8).permute(2, 0, 3, 1, 4).reshape(3, 8, 8).permute(1, 2, 0)
-        assert torch.equal(drivers.to_uint8_hwc(img)[k], r)
+        assert np.array_equal(got[k].numpy(), layout_grid(img[k:k + 1], grid_w=1, grid_h=1))
 
 
 class _StubG(torch.nn.Module):
@@ -91,24 +92,20 @@ def test_batched_frames_equal_per_frame_loop(F, batch, mesh):
 
 
 # ------------------------------------------------------------------------------------------------ row f2: shape extraction
-def ref_create_samples(N=256, voxel_origin=[0, 0, 0], cube_length=2.0):
-    """gen_samples_next3d.py:80-102, verbatim"""
-    voxel_origin = np.array(voxel_origin) - cube_length / 2
-    voxel_size = cube_length / (N - 1)
-    overall_index = torch.arange(0, N ** 3, 1, out=torch.LongTensor())
-    samples = torch.zeros(N ** 3, 3)
-    samples[:, 2] = overall_index % N
-    samples[:, 1] = (overall_index.float() / N) % N
-    samples[:, 0] = ((overall_index.float() / N) / N) % N
-    samples[:, 0] = (samples[:, 0] * voxel_size) + voxel_origin[2]
-    samples[:, 1] = (samples[:, 1] * voxel_size) + voxel_origin[1]
-    samples[:, 2] = (samples[:, 2] * voxel_size) + voxel_origin[0]
-    return samples.unsqueeze(0), voxel_origin, voxel_size
+def _reference_scripts():
+    """The reference's own gen_samples_next3d / gen_videos_next3d modules (through the oracle's import shims)."""
+    from oracle import ref_shim
+    ref_shim.import_reference()
+    with ref_shim.in_scratch():
+        import gen_samples_next3d
+        import gen_videos_next3d
+    return gen_samples_next3d, gen_videos_next3d
 
 
+@needs_ref
 @pytest.mark.parametrize('N', [17, 64])
 def test_chunked_samples_are_slices_of_the_reference_grid(N):
-    ref = ref_create_samples(N, cube_length=1.0)[0]
+    ref = _reference_scripts()[0].create_samples(N=N, voxel_origin=[0, 0, 0], cube_length=1.0)[0]
     assert torch.equal(drivers.create_samples(N, 1.0), ref)
     for head, n in [(0, 1000), (N ** 3 - 777, 777), (12345 % N ** 3, 2048)]:
         n = min(n, N ** 3 - head)
@@ -126,10 +123,13 @@ def test_large_index_rounding_like_the_reference():
 
 
 def test_trim_matches_script():
+    """flip along axis 0, then a border of int(30 * R / 256) voxels on all six faces set to -1000 (gen_samples_next3d.py:226-238)."""
     R = 64
     g = torch.Generator().manual_seed(3)
     sig = torch.randn(R, R, R, generator=g)
-    ref = np.flip(sig.numpy().copy(), 0).copy()                           # gen_samples_next3d.py:226-238
+    ref = sig.numpy()[::-1].copy()
     pad = int(30 * R / 256)
-    ref[:pad] = -1000; ref[-pad:] = -1000; ref[:, :pad] = -1000; ref[:, -pad:] = -1000; ref[:, :, :pad] = -1000; ref[:, :, -pad:] = -1000
+    inner = np.zeros((R, R, R), bool)
+    inner[pad:R - pad, pad:R - pad, pad:R - pad] = True
+    ref[~inner] = -1000
     assert np.array_equal(drivers.trim_sigma_grid(sig.clone(), R).numpy(), ref)

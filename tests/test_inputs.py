@@ -1,5 +1,5 @@
 """Row f3 of SURVEY.md section 8: native .obj / landmark parsers vs the reference's own parsing code (gen_samples_next3d.py:165-178,
-restated verbatim below as the oracle), bit-exact in float32.  CPU only."""
+restated below as the oracle), bit-exact in float32.  CPU only."""
 import os
 
 import numpy as np
@@ -12,17 +12,10 @@ REF_DEMO = '/root/reference/data/demo'
 
 
 def ref_parse_obj(path):
-    """gen_samples_next3d.py:165-174"""
-    v = []
-    with open(path, 'r') as f:
-        while True:
-            line = f.readline()
-            if line == '':
-                break
-            if line[:2] == 'v ':
-                v.append([float(x) for x in line.split()[1:]])
-    v = np.array(v).reshape((-1, 3))
-    return torch.from_numpy(v).float().unsqueeze(0)
+    """What gen_samples_next3d.py:165-174 computes, restated: the numbers after the tag of every line whose first two characters
+    are 'v ', through float(), flattened to [V, 3] float64, then .float()."""
+    rows = [[float(tok) for tok in ln.split()[1:]] for ln in open(path, 'r').read().split('\n') if ln[:2] == 'v ']
+    return torch.from_numpy(np.array(rows, dtype=np.float64).reshape(-1, 3)).float()[None]
 
 
 def _write_obj(path, rng, n=500):

@@ -13,16 +13,11 @@ from next3d_b200 import inputs  # noqa: E402
 
 
 def ref_frame(obj, kpt):
-    v = []
-    with open(obj, 'r') as f:
-        while True:
-            line = f.readline()
-            if line == '':
-                break
-            if line[:2] == 'v ':
-                v.append([float(x) for x in line.split()[1:]])
-    v = torch.from_numpy(np.array(v).reshape((-1, 3))).float().unsqueeze(0)
-    return torch.cat((v, torch.from_numpy(np.loadtxt(kpt)).float().unsqueeze(0)), 1)
+    """The scripts' per-frame parsing (gen_samples_next3d.py:165-178) restated in Python: float() of every token of the 'v ' lines,
+    np.loadtxt for the landmarks, torch.cat."""
+    rows = [[float(tok) for tok in ln.split()[1:]] for ln in open(obj, 'r').read().split('\n') if ln[:2] == 'v ']
+    v = torch.from_numpy(np.array(rows).reshape(-1, 3)).float()[None]
+    return torch.cat((v, torch.from_numpy(np.loadtxt(kpt)).float()[None]), 1)
 
 
 def main():
