@@ -1,0 +1,881 @@
+// Fused volume renderer for sm_100a, warp-specialised: ray generation, stratified depths, tri-plane bilinear fetch (+ mean over
+// planes), MLP decoder (32 -> 64 softplus -> 1 + 32, sigmoid) on tcgen05 tensor cores, coarse compositing weights, importance
+// resampling, sort-merge of coarse + fine samples and final alpha compositing in ONE persistent kernel.  Replaces
+// RaySampler.forward (ray_sampler.py:24-63), ImportanceRenderer.forward (renderer.py:95-268), OSGDecoder.forward
+// (triplane_next3d.py:359-371) and MipRayMarcher2.run_forward (ray_marcher.py:27-66).
+//
+// One CTA per SM, 16 warps:
+//   warps  0-7   E ("epilogue") : two sets of four; warp w owns TMEM lanes 32*(w%4).., set s = w/4 owns hidden units 32s..32s+31 and
+//                colour channels 16s..16s+15.  Thread = tile row = one depth sample of one ray in every tile of its group.
+//   warps  8-14  G ("gather")   : build the layer-1 A operand in shared memory; work item = 32 rows (a quarter) of a tile, items
+//                dealt round-robin to the seven warps; 12 bilinear taps per sample fetched as 128-bit loads, 8 lanes x 4
+//                channels per sample.
+//   warp  15     MMA issuer (one lane) + TMEM allocation.
+// Work unit: a GROUP = 128/L rays (a 4x2 or 2x2 pixel block) x L lanes each, L = 16 (<= 48 samples per pass) or 32 (<= 96).
+// A pass of a group is T = ceil(D / L) <= 3 tiles of 128 rows; row = ray_slot * L + j holds sample k = tile * L + j of that ray,
+// so a ray's samples always sit in the same L lanes of the same warp and every per-ray phase (transmittance scan, PDF/CDF,
+// inverse-CDF sampling, rank merge, weighted colour sum) runs on registers + warp shuffles, no CTA-wide barrier anywhere.
+// Tile stream of a CTA: C(0) | C(1) F(0) | C(2) F(1) | ...  (coarse tiles of group r+1 are issued before the fine tiles of
+// group r, so the importance sampling of a group never stalls the gather warps).
+//
+// TMEM (512 columns): [0,64) layer-1 accumulator; [64,192) two hidden-activation buffers (bf16 hi words | lo words) that are the
+// A operand of layer 2 (tcgen05.mma with A in tensor memory: no shared-memory round trip, no swizzle); [192,224) two sigma
+// accumulators (N = 16, column 0 used); [224,512) nine colour-logit slots of 32 columns (coarse of two groups + fine of one):
+// the colour logits never leave TMEM until the final weights are known, then each thread applies the sigmoid and accumulates
+// coefficient x colour for its own rows.  Decoder arithmetic: bf16x3 (hi*hi + hi*lo + lo*hi), fp32 accumulate.
+#include "common.cuh"
+#include "../../include/next3d_b200.h"
+#include "tc_ptx.cuh"
+#include "render_common.cuh"
+
+namespace {
+using namespace n3d_tc;
+using namespace n3d_rc;
+
+constexpr int kEWarps = 8, kGWarps = 7;
+constexpr int kWarps = kEWarps + kGWarps + 1;
+constexpr int kThreads = kWarps * 32;           // 512 (16 warps -> 128 registers per thread)
+constexpr int kMaxT = 3;                        // tiles per pass
+constexpr unsigned FULL = 0xffffffffu;
+
+constexpr uint32_t kColL1 = 0, kColH = 64, kColSig = 192, kColSlot = 224;
+
+// shared-memory byte offsets (base 1024-aligned)
+constexpr int kOffW0hi = 0, kOffW0lo = 4096, kOffWchi = 8192, kOffWclo = 12288, kOffWshi = 16384, kOffWslo = 18432;
+constexpr int kOffF = 20480;                                    // 2 x (hi 8 KiB | lo 8 KiB)
+constexpr int kOffTaps = kOffF + 2 * 16384;                     // 8 warps x [12][32] x (offset, weight)
+constexpr int kTapBytesPerWarp = 12 * 32 * 8;
+constexpr int kOffEscr = kOffTaps + kGWarps * kTapBytesPerWarp; // per-E-warp scratch
+constexpr int kEscrFloats = 896;
+constexpr int kOffTfine = kOffEscr + kEWarps * kEscrFloats * 4; // [2][rays per group][Df] fine depths for the gather warps
+constexpr int kTfineFloats = 384;
+constexpr int kOffBias = kOffTfine + 2 * kTfineFloats * 4;      // b0 * log2e [64] | b1 colour [32] | b1 sigma [1] (+pad)
+constexpr int kOffBar = kOffBias + (64 + 32 + 16) * 4;
+constexpr int kNumBars = 16;
+constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16;
+
+enum { BAR_FFULL = 0, BAR_FEMPTY = 2, BAR_L1DONE = 4, BAR_L1FREE = 5, BAR_HFULL = 6, BAR_L2DONE = 8, BAR_CFREE = 10, BAR_FFREE = 12,
+       BAR_FINE = 13 };
+
+struct FusedK {
+    N3DRender p;
+    int M;                       // rays per image
+    float delta_coarse, scale;
+    int Tc, Tf;                  // tiles per coarse / fine pass
+    int gw, log2gw;              // pixel block of a group: gw x 2
+    int blocks_x, gpi;           // group map: blocks of 4 x 8 groups, groups per image (padded)
+    long long total_groups;
+    int mode;                    // diagnostics: bit 0 = skip the plane loads (gather floor off), bit 1 = skip activations
+};
+
+// ---------------------------------------------------------------------------------------------------------------- group -> rays
+struct RayId {
+    int n, row, col;
+    bool ok;
+    long long gr;
+};
+__device__ __forceinline__ RayId ray_of(const FusedK& K, long long gg, int rs) {
+    RayId r;
+    const int n = (int)(gg / K.gpi);
+    const int q = (int)(gg - (long long)n * K.gpi);
+    const int blk = q >> 5, inb = q & 31;
+    const int byi = blk / K.blocks_x, bxi = blk - byi * K.blocks_x;
+    const int tx = bxi * 4 + (inb & 3), ty = byi * 8 + (inb >> 2);
+    r.col = tx * K.gw + (rs & (K.gw - 1));
+    r.row = ty * 2 + (rs >> K.log2gw);
+    r.n = n;
+    r.ok = r.col < K.p.res && r.row < K.p.res;
+    r.gr = (long long)n * K.M + (long long)r.row * K.p.res + r.col;
+    return r;
+}
+
+struct Ray {
+    float ox, oy, oz, dx, dy, dz;
+    uint32_t img4;
+    long long gr;
+    bool ok;
+};
+// ray_sampler.py:43-63 for pixel (row i, column j)
+__device__ __forceinline__ Ray make_ray(const FusedK& K, long long gg, int rs) {
+    const N3DRender& P = K.p;
+    const RayId id = ray_of(K, gg, rs);
+    Ray r;
+    r.ok = id.ok;
+    r.gr = id.gr;
+    r.img4 = (uint32_t)id.n * (uint32_t)(3 * P.PH * P.PW * 8);
+    r.ox = r.oy = r.oz = r.dx = r.dy = r.dz = 0.f;
+    if (id.ok) {
+        const float inv = 1.f / (float)P.res, half = 0.5f / (float)P.res;
+        const float xc = (float)id.col * inv + half, yc = (float)id.row * inv + half;
+        const float* I = P.intrinsics + id.n * 9;
+        const float fx = __ldg(I), sk = __ldg(I + 1), cx = __ldg(I + 2), fy = __ldg(I + 4), cy = __ldg(I + 5);
+        const float xl = (xc - cx + cy * sk / fy - sk * yc / fy) / fx;
+        const float yl = (yc - cy) / fy;
+        const float* C = P.cam2world + id.n * 16;
+        float wv[3], o[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            wv[a] = __ldg(C + a * 4) * xl + __ldg(C + a * 4 + 1) * yl + __ldg(C + a * 4 + 2) + __ldg(C + a * 4 + 3);
+            o[a] = __ldg(C + a * 4 + 3);
+            wv[a] -= o[a];
+        }
+        const float nrm = fmaxf(sqrtf(wv[0] * wv[0] + wv[1] * wv[1] + wv[2] * wv[2]), 1e-12f);
+        r.ox = o[0]; r.oy = o[1]; r.oz = o[2];
+        r.dx = wv[0] / nrm; r.dy = wv[1] / nrm; r.dz = wv[2] / nrm;
+    }
+    return r;
+}
+
+__device__ __forceinline__ float coarse_depth(const FusedK& K, uint64_t seed, long long gr, int k) {
+    const N3DRender& P = K.p;
+    const float u = P.u_coarse ? __ldg(P.u_coarse + gr * P.depth_coarse + k) : hash_uniform(seed, (uint64_t)(gr * P.depth_coarse + k));
+    return linspace_at(P.ray_start, P.ray_end, P.depth_coarse, k) + u * K.delta_coarse;
+}
+
+// ---------------------------------------------------------------------------------------------------------------- gather warps
+// 12 bilinear taps of one sample (3 planes x 4 corners; plane 0 <- (x,y), 1 <- (x,z), 2 <- (z,y); grid_sample zeros padding,
+// align_corners=False): float4-index of the texel's first channel group + weight.  Zero-weight taps all point at texel 0.
+__device__ __forceinline__ void setup_taps(uint2* __restrict__ taps, int lane, float px, float py, float pz, bool valid, uint32_t img4, int PH,
+                                           int PW, float scale) {
+    const float x = scale * px, y = scale * py, z = scale * pz;
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl) {
+        const float gx = pl == 2 ? z : x, gy = pl == 1 ? z : y;
+        const float ix = ((gx + 1.f) * (float)PW - 1.f) * 0.5f, iy = ((gy + 1.f) * (float)PH - 1.f) * 0.5f;
+        const float flx = floorf(ix), fly = floorf(iy);
+        const float fx = ix - flx, fy = iy - fly;
+        const int x0 = (int)fminf(fmaxf(flx, -2.f), (float)PW), y0 = (int)fminf(fmaxf(fly, -2.f), (float)PH);
+        const uint32_t pbase = img4 + (uint32_t)(pl * PH * PW) * 8u;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int xi = x0 + (c & 1), yi = y0 + (c >> 1);
+            const float wx = (c & 1) ? fx : 1.f - fx, wy = (c >> 1) ? fy : 1.f - fy;
+            const bool inside = valid && xi >= 0 && xi < PW && yi >= 0 && yi < PH;
+            const float w = inside ? wx * wy : 0.f;
+            const uint32_t off = inside ? pbase + (uint32_t)(yi * PW + xi) * 8u : 0u;
+            taps[(pl * 4 + c) * 32 + lane] = make_uint2(off, __float_as_uint(w));
+        }
+    }
+}
+
+// 32 samples whose taps sit in `taps`: lanes = 4 samples x 8 channel groups per step; the mean feature goes straight into the
+// K-major SWIZZLE_64B bf16 (hi, lo) A-operand tile rows row0..row0+31.
+__device__ __forceinline__ void gather_rows(const float4* __restrict__ planes4, const uint2* __restrict__ taps, uint8_t* __restrict__ f_hi,
+                                            uint8_t* __restrict__ f_lo, int row0, int lane, bool skip_loads) {
+    const int c4 = lane & 7;
+#pragma unroll 1
+    for (int it = 0; it < 8; ++it) {
+        const int s = it * 4 + (lane >> 3);
+        uint2 tp[12];
+        float4 v[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) tp[i] = taps[i * 32 + s];
+        if (!skip_loads) {
+#pragma unroll
+            for (int i = 0; i < 12; ++i) v[i] = __ldg(planes4 + tp[i].x + c4);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 12; ++i) v[i] = make_float4(__uint_as_float(tp[i].x), 1.f, 2.f, 3.f);
+        }
+        float4 a[3];
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl) {
+            float w = __uint_as_float(tp[pl * 4].y);
+            a[pl] = make_float4(w * v[pl * 4].x, w * v[pl * 4].y, w * v[pl * 4].z, w * v[pl * 4].w);
+#pragma unroll
+            for (int c = 1; c < 4; ++c) {
+                w = __uint_as_float(tp[pl * 4 + c].y);
+                const float4 t = v[pl * 4 + c];
+                a[pl].x = fmaf(w, t.x, a[pl].x); a[pl].y = fmaf(w, t.y, a[pl].y); a[pl].z = fmaf(w, t.z, a[pl].z); a[pl].w = fmaf(w, t.w, a[pl].w);
+            }
+        }
+        const float third = 1.f / 3.f;
+        const float f0 = ((a[0].x + a[1].x) + a[2].x) * third, f1 = ((a[0].y + a[1].y) + a[2].y) * third;
+        const float f2 = ((a[0].z + a[1].z) + a[2].z) * third, f3 = ((a[0].w + a[1].w) + a[2].w) * third;
+        uint32_t h0, l0, h1, l1;
+        split_bf16x2(f0, f1, h0, l0);
+        split_bf16x2(f2, f3, h1, l1);
+        const uint32_t off = sw64_off(row0 + s, c4 * 8);
+        *reinterpret_cast<uint2*>(f_hi + off) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(f_lo + off) = make_uint2(l0, l1);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------- per-ray math
+// A ray's samples live in the L lanes [lane & ~(L-1), +L) of one warp, sample k = t * L + j in register slot t of lane j.
+template <int L>
+__device__ __forceinline__ float seg_next(float v, float v_next_slot, int lane) {      // value of sample k + 1
+    const float a = __shfl_down_sync(FULL, v, 1);
+    const float b = __shfl_sync(FULL, v_next_slot, lane & ~(L - 1));
+    return ((lane & (L - 1)) == L - 1) ? b : a;
+}
+template <int L>
+__device__ __forceinline__ float seg_prev(float v, float v_prev_slot, int lane) {      // value of sample k - 1
+    const float a = __shfl_up_sync(FULL, v, 1);
+    const float b = __shfl_sync(FULL, v_prev_slot, lane | (L - 1));
+    return ((lane & (L - 1)) == 0) ? b : a;
+}
+template <int L>
+__device__ __forceinline__ float seg_sum(float v) {
+#pragma unroll
+    for (int o = L / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+template <int L, int NT, bool MUL>
+__device__ __forceinline__ void seg_scan(float (&x)[NT], int lane) {                  // inclusive scan in sample order
+    float carry = MUL ? 1.f : 0.f;
+    const int j = lane & (L - 1);
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+        float v = x[t];
+#pragma unroll
+        for (int o = 1; o < L; o <<= 1) {
+            const float up = __shfl_up_sync(FULL, v, o);
+            if (j >= o) v = MUL ? v * up : v + up;
+        }
+        v = MUL ? v * carry : v + carry;
+        x[t] = v;
+        carry = __shfl_sync(FULL, v, lane | (L - 1));
+    }
+}
+
+// MipRayMarcher2 weights (ray_marcher.py:27-46) of a depth-sorted list of `cnt` samples (d, sg):
+//   alpha_k = 1 - exp(-softplus((s_k + s_k+1)/2 - 1) * (t_k+1 - t_k)),  T_k = prod_{i<k} (1 - alpha_i + 1e-10),  w_k = alpha_k T_k
+// w_k = 0 for k >= cnt - 1.  tmid_k = (t_k + t_k+1) / 2.
+template <int L, int NT>
+__device__ __forceinline__ void march_weights(const float (&d)[NT], const float (&sg)[NT], int cnt, int lane, float (&w)[NT], float (&tmid)[NT]) {
+    const int j = lane & (L - 1);
+    float fac[NT], al[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+        const float dn = seg_next<L>(d[t], t + 1 < NT ? d[t + 1] : 0.f, lane);
+        const float sn = seg_next<L>(sg[t], t + 1 < NT ? sg[t + 1] : 0.f, lane);
+        const int k = t * L + j;
+        float alpha = 0.f;
+        if (k < cnt - 1) {
+            const float delta = dn - d[t];
+            const float dens = softplus_fast((sg[t] + sn) * 0.5f - 1.f);
+            alpha = 1.f - ex2_approx(-kLog2e * (dens * delta));
+        }
+        al[t] = alpha;
+        fac[t] = k < cnt - 1 ? (1.f - alpha + 1e-10f) : 1.f;
+        tmid[t] = (d[t] + dn) * 0.5f;
+    }
+    seg_scan<L, NT, true>(fac, lane);
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+        const float ex = seg_prev<L>(fac[t], t > 0 ? fac[t - 1] : 1.f, lane);
+        w[t] = al[t] * ((t == 0 && j == 0) ? 1.f : ex);
+    }
+}
+
+struct Smem {
+    uint8_t* base;
+    __device__ __forceinline__ uint32_t bar(int i) const { return smem_u32(base + kOffBar + i * 8); }
+};
+
+// ---------------------------------------------------------------------------------------------------------------- the kernel
+template <int L>
+__global__ void __launch_bounds__(kThreads, 1) render_fused_kernel(const __grid_constant__ FusedK K) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    constexpr int RPW = 32 / L;                 // rays per warp
+    const N3DRender& P = K.p;
+    Smem S;
+    S.base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* const sb = S.base;
+    float* const sB0 = reinterpret_cast<float*>(sb + kOffBias);         // b0 * log2(e)
+    float* const sB1c = sB0 + 64;                                        // colour biases (outputs 1..32)
+    float* const sB1s = sB1c + 32;                                       // sigma bias
+    float* const sTfine = reinterpret_cast<float*>(sb + kOffTfine);
+    uint32_t* const sTmem = reinterpret_cast<uint32_t*>(sb + kOffBar + kNumBars * 8);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int Dc = P.depth_coarse, Df = P.depth_fine, Dt = Dc + Df;
+    const int Tc = K.Tc, Tf = K.Tf;
+    const uint64_t seed = P.seed_ptr ? (P.seed + __ldg(reinterpret_cast<const unsigned long long*>(P.seed_ptr))) : P.seed;
+
+    // this CTA's contiguous chunk of groups
+    const long long g_begin = (K.total_groups * blockIdx.x) / gridDim.x;
+    const int n_groups = (int)((K.total_groups * (blockIdx.x + 1)) / gridDim.x - g_begin);
+
+    // ---- one-time setup
+    if (tid == 0) {
+        mbar_init(S.bar(BAR_FFULL + 0), 4); mbar_init(S.bar(BAR_FFULL + 1), 4);
+        mbar_init(S.bar(BAR_FEMPTY + 0), 1); mbar_init(S.bar(BAR_FEMPTY + 1), 1);
+        mbar_init(S.bar(BAR_L1DONE), 1);
+        mbar_init(S.bar(BAR_L1FREE), kEWarps);
+        mbar_init(S.bar(BAR_HFULL + 0), kEWarps); mbar_init(S.bar(BAR_HFULL + 1), kEWarps);
+        mbar_init(S.bar(BAR_L2DONE + 0), 1); mbar_init(S.bar(BAR_L2DONE + 1), 1);
+        mbar_init(S.bar(BAR_CFREE + 0), kEWarps); mbar_init(S.bar(BAR_CFREE + 1), kEWarps);
+        mbar_init(S.bar(BAR_FFREE), kEWarps);
+        mbar_init(S.bar(BAR_FINE + 0), 4); mbar_init(S.bar(BAR_FINE + 1), 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kWarps - 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = tid; i < kHidden * kFeat; i += kThreads) {               // W0 [64][32]: row = hidden unit, K = 32 (SWIZZLE_64B)
+        const int n = i / kFeat, k = i - n * kFeat;
+        __nv_bfloat16 h, l;
+        split_bf16(__ldg(P.w0 + i), h, l);
+        *reinterpret_cast<__nv_bfloat16*>(sb + kOffW0hi + sw64_off(n, k * 2)) = h;
+        *reinterpret_cast<__nv_bfloat16*>(sb + kOffW0lo + sw64_off(n, k * 2)) = l;
+    }
+    for (int i = tid; i < 32 * kHidden; i += kThreads) {                  // colour rows of W1 (outputs 1..32) [32][64] (SWIZZLE_128B)
+        const int n = i / kHidden, k = i - n * kHidden;
+        __nv_bfloat16 h, l;
+        split_bf16(__ldg(P.w1 + (n + 1) * kHidden + k), h, l);
+        *reinterpret_cast<__nv_bfloat16*>(sb + kOffWchi + sw128_off(n, k * 2)) = h;
+        *reinterpret_cast<__nv_bfloat16*>(sb + kOffWclo + sw128_off(n, k * 2)) = l;
+    }
+    for (int i = tid; i < 16 * kHidden; i += kThreads) {                  // sigma row of W1 (output 0) padded to N = 16
+        const int n = i / kHidden, k = i - n * kHidden;
+        __nv_bfloat16 h, l;
+        split_bf16(n == 0 ? __ldg(P.w1 + k) : 0.f, h, l);
+        *reinterpret_cast<__nv_bfloat16*>(sb + kOffWshi + sw128_off(n, k * 2)) = h;
+        *reinterpret_cast<__nv_bfloat16*>(sb + kOffWslo + sw128_off(n, k * 2)) = l;
+    }
+    for (int i = tid; i < kHidden; i += kThreads) sB0[i] = __ldg(P.b0 + i) * kLog2e;
+    for (int i = tid; i < 32; i += kThreads) sB1c[i] = __ldg(P.b1 + 1 + i);
+    if (tid == 0) sB1s[0] = __ldg(P.b1);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *sTmem;
+
+    // ============================================================================================================ MMA warp
+    if (warp == kWarps - 1) {
+        if (lane == 0) {
+            const uint64_t dhi64 = umma_desc_hi(32), dhi128 = umma_desc_hi(64);
+            const uint32_t id64 = umma_idesc_bf16(64), id32 = umma_idesc_bf16(32), id16 = umma_idesc_bf16(16);
+            const uint32_t w0h = smem_u32(sb + kOffW0hi), w0l = smem_u32(sb + kOffW0lo);
+            const uint32_t wch = smem_u32(sb + kOffWchi), wcl = smem_u32(sb + kOffWclo), wsh = smem_u32(sb + kOffWshi), wsl = smem_u32(sb + kOffWslo);
+            // slot of the tile before the current one (its layer 2 is issued after the current tile's layer 1)
+            int prev_slot = -1, prev_wait = 0, prev_r = 0;      // prev_wait: 0 none, 1 coarse-slot reuse, 2 fine-slot reuse
+            int i = 0;
+            auto layer1 = [&](int ti) {
+                const int b = ti & 1;
+                mbar_wait(S.bar(BAR_FFULL + b), (uint32_t)((ti >> 1) & 1), nullptr, 0);
+                if (ti > 0) mbar_wait(S.bar(BAR_L1FREE), (uint32_t)((ti - 1) & 1), nullptr, 0);
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(sb + kOffF + b * 16384), a_lo = a_hi + 8192;
+#pragma unroll
+                for (int k16 = 0; k16 < kFeat / 16; ++k16) {
+                    const uint32_t ko = (uint32_t)k16 * 32u;
+                    umma_bf16(tmem + kColL1, umma_desc(a_hi + ko, dhi64), umma_desc(w0h + ko, dhi64), id64, k16 != 0);
+                    umma_bf16(tmem + kColL1, umma_desc(a_hi + ko, dhi64), umma_desc(w0l + ko, dhi64), id64, 1u);
+                    umma_bf16(tmem + kColL1, umma_desc(a_lo + ko, dhi64), umma_desc(w0h + ko, dhi64), id64, 1u);
+                }
+                umma_commit(S.bar(BAR_FEMPTY + b));
+                umma_commit(S.bar(BAR_L1DONE));
+            };
+            auto layer2 = [&](int tj, int slot, int wait_kind, int r) {
+                const int b = tj & 1;
+                mbar_wait(S.bar(BAR_HFULL + b), (uint32_t)((tj >> 1) & 1), nullptr, 0);
+                if (wait_kind == 1) mbar_wait(S.bar(BAR_CFREE + (r & 1)), (uint32_t)(((r >> 1) - 1) & 1), nullptr, 0);
+                if (wait_kind == 2) mbar_wait(S.bar(BAR_FFREE), (uint32_t)((r - 1) & 1), nullptr, 0);
+                tc_fence_after();
+                const uint32_t hA = tmem + kColH + 64u * b;
+                const uint32_t dC = tmem + kColSlot + 32u * slot, dS = tmem + kColSig + 16u * b;
+#pragma unroll
+                for (int k16 = 0; k16 < kHidden / 16; ++k16) {
+                    const uint32_t ko = (uint32_t)k16 * 32u, ka = (uint32_t)k16 * 8u;
+                    umma_bf16_ts(dC, hA + ka, umma_desc(wch + ko, dhi128), id32, k16 != 0);
+                    umma_bf16_ts(dC, hA + ka, umma_desc(wcl + ko, dhi128), id32, 1u);
+                    umma_bf16_ts(dC, hA + 32u + ka, umma_desc(wch + ko, dhi128), id32, 1u);
+                    umma_bf16_ts(dS, hA + ka, umma_desc(wsh + ko, dhi128), id16, k16 != 0);
+                    umma_bf16_ts(dS, hA + ka, umma_desc(wsl + ko, dhi128), id16, 1u);
+                    umma_bf16_ts(dS, hA + 32u + ka, umma_desc(wsh + ko, dhi128), id16, 1u);
+                }
+                umma_commit(S.bar(BAR_L2DONE + b));
+            };
+            for (int r = 0; r <= n_groups; ++r) {
+                if (r < n_groups)
+                    for (int t = 0; t < Tc; ++t) {
+                        layer1(i);
+                        if (prev_slot >= 0) layer2(i - 1, prev_slot, prev_wait, prev_r);
+                        prev_slot = (r & 1) * 3 + t; prev_wait = (t == 0 && r >= 2) ? 1 : 0; prev_r = r;
+                        ++i;
+                    }
+                if (r >= 1)
+                    for (int t = 0; t < Tf; ++t) {
+                        // fine tile directly behind its own group's coarse tiles (single-group CTA): the gather of this tile
+                        // waits for the importance sampling, which waits for the previous tile's layer 2
+                        if (prev_slot >= 0 && prev_slot < 6 && prev_r == r - 1) { layer2(i - 1, prev_slot, prev_wait, prev_r); prev_slot = -1; }
+                        layer1(i);
+                        if (prev_slot >= 0) layer2(i - 1, prev_slot, prev_wait, prev_r);
+                        prev_slot = 6 + t; prev_wait = (t == 0 && r - 1 >= 1) ? 2 : 0; prev_r = r - 1;
+                        ++i;
+                    }
+            }
+            if (prev_slot >= 0) layer2(i - 1, prev_slot, prev_wait, prev_r);
+        }
+    }
+    // ============================================================================================================ gather warps
+    else if (warp >= kEWarps) {
+        const int gw = warp - kEWarps;
+        uint2* const taps = reinterpret_cast<uint2*>(sb + kOffTaps + gw * kTapBytesPerWarp);
+        const float4* const planes4 = reinterpret_cast<const float4*>(P.planes);
+        int next_item = gw;                                   // item = tile * 4 + quarter
+        auto item = [&](int ti, int q, bool fine, int r, int t) {
+            const int row = q * 32 + lane, rs = row / L, j = row & (L - 1);
+            const Ray ray = make_ray(K, g_begin + r, rs);
+            const int k = t * L + j;
+            const bool valid = ray.ok && k < (fine ? Df : Dc);
+            float depth = 0.f;
+            if (fine) {
+                mbar_wait(S.bar(BAR_FINE + (r & 1)), (uint32_t)((r >> 1) & 1), nullptr, 0);
+                if (valid) depth = sTfine[(r & 1) * kTfineFloats + rs * Df + k];
+            } else if (valid) {
+                depth = coarse_depth(K, seed, ray.gr, k);
+            }
+            setup_taps(taps, lane, ray.ox + depth * ray.dx, ray.oy + depth * ray.dy, ray.oz + depth * ray.dz, valid, ray.img4, P.PH, P.PW, K.scale);
+            __syncwarp();
+            const int b = ti & 1;
+            if (ti >= 2) mbar_wait(S.bar(BAR_FEMPTY + b), (uint32_t)(((ti >> 1) - 1) & 1), nullptr, 0);
+            gather_rows(planes4, taps, sb + kOffF + b * 16384, sb + kOffF + b * 16384 + 8192, q * 32, lane, (K.mode & 1) != 0);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(S.bar(BAR_FFULL + b));
+        };
+        auto tile = [&](int ti, bool fine, int r, int t) {
+            while (next_item < ti * 4 + 4) {
+                item(ti, next_item - ti * 4, fine, r, t);
+                next_item += kGWarps;
+            }
+        };
+        int i = 0;
+        for (int r = 0; r <= n_groups; ++r) {
+            if (r < n_groups)
+                for (int t = 0; t < Tc; ++t, ++i) tile(i, false, r, t);
+            if (r >= 1)
+                for (int t = 0; t < Tf; ++t, ++i) tile(i, true, r - 1, t);
+        }
+    }
+    // ============================================================================================================ epilogue warps
+    else {
+        const int eset = warp >> 2, q = warp & 3;
+        const int row = q * 32 + lane, rs = row / L, j = row & (L - 1), rw = lane / L;
+        const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+        float* const es = reinterpret_cast<float*>(sb + kOffEscr) + warp * kEscrFloats;
+        // per-warp scratch (floats): sd | sg | wb : RPW x (Dt + 2) each ; tcs : RPW x Dc ; tfs : RPW x Df ; hist : RPW x (Dc + 1)
+        const int strD = Dt + 2;
+        float* const s_sd = es + rw * strD;                         // sorted depths (aliases the cdf during importance sampling)
+        float* const s_sg = es + RPW * strD + rw * strD;
+        float* const s_wb = es + 2 * RPW * strD + rw * strD;
+        float* const s_tc = es + 3 * RPW * strD + rw * Dc;
+        float* const s_tf = es + 3 * RPW * strD + RPW * Dc + rw * Df;
+        int* const s_hist = reinterpret_cast<int*>(es + 3 * RPW * strD + RPW * (Dc + Df)) + rw * (Dc + 1);
+        const bool skip_act = (K.mode & 2) != 0;
+
+        // state of the group in its fine phase (cur) and of the group in its coarse phase (nxt)
+        float cur_tc[kMaxT], cur_sc[kMaxT], cur_tf[kMaxT], cur_sf[kMaxT];
+        float nxt_tc[kMaxT], nxt_sc[kMaxT], nxt_tf[kMaxT];
+        long long cur_gr = 0, nxt_gr = 0;
+        bool cur_ok = false, nxt_ok = false;
+#pragma unroll
+        for (int t = 0; t < kMaxT; ++t) { cur_tc[t] = cur_sc[t] = cur_tf[t] = cur_sf[t] = nxt_tc[t] = nxt_sc[t] = nxt_tf[t] = 0.f; }
+        float dmin = INFINITY, dmax = -INFINITY;
+
+        // ---- layer-1 epilogue of tile ti: softplus(acc + b0) -> bf16 (hi, lo) words -> hidden buffer (A operand of layer 2)
+        auto epi1 = [&](int ti) {
+            mbar_wait(S.bar(BAR_L1DONE), (uint32_t)(ti & 1), nullptr, 0);
+            tc_fence_after();
+            uint32_t a[32];
+            tmem_ld16_nowait(tlane + kColL1 + 32u * eset, a);
+            tmem_ld16_nowait(tlane + kColL1 + 32u * eset + 16u, a + 16);
+            tmem_wait_ld();
+            reg_fence16(a);
+            reg_fence16(a + 16);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(S.bar(BAR_L1FREE));
+            uint32_t hi[16], lo[16];
+            const float4* b4 = reinterpret_cast<const float4*>(sB0 + 32 * eset);
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) {
+                const float4 bb = b4[c4];
+                float y0 = fmaf(__uint_as_float(a[c4 * 4]), kLog2e, bb.x), y1 = fmaf(__uint_as_float(a[c4 * 4 + 1]), kLog2e, bb.y);
+                float y2 = fmaf(__uint_as_float(a[c4 * 4 + 2]), kLog2e, bb.z), y3 = fmaf(__uint_as_float(a[c4 * 4 + 3]), kLog2e, bb.w);
+                if (!skip_act) { y0 = softplus_from_log2(y0); y1 = softplus_from_log2(y1); y2 = softplus_from_log2(y2); y3 = softplus_from_log2(y3); }
+                split_bf16x2(y0, y1, hi[c4 * 2], lo[c4 * 2]);
+                split_bf16x2(y2, y3, hi[c4 * 2 + 1], lo[c4 * 2 + 1]);
+            }
+            const uint32_t hb = tlane + kColH + 64u * (ti & 1);
+            tmem_st16(hb + 16u * eset, hi);
+            tmem_st16(hb + 32u + 16u * eset, lo);
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(S.bar(BAR_HFULL + (ti & 1)));
+        };
+        auto read_sigma = [&](int tj) -> float {
+            mbar_wait(S.bar(BAR_L2DONE + (tj & 1)), (uint32_t)((tj >> 1) & 1), nullptr, 0);
+            tc_fence_after();
+            uint32_t v;
+            tmem_ld1_nowait(tlane + kColSig + 16u * (tj & 1), v);
+            tmem_wait_ld();
+            reg_fence1(v);
+            return __uint_as_float(v) + sB1s[0];
+        };
+
+        // ---- coarse weights -> smoothed pdf -> cdf -> inverse-CDF fine depths (renderer.py:209-268) for the group in `nxt`
+        auto importance = [&](int r) {
+            float w[kMaxT], tm[kMaxT];
+            march_weights<L, kMaxT>(nxt_tc, nxt_sc, Dc, lane, w, tm);
+            // max_pool1d(k2,s1,pad1) -> avg_pool1d(k2,s1) -> + 0.01; entries [1:-1] => pdf weights at k = 1 .. Dc-3, + 1e-5
+            const int nw = Dc - 3;
+            float c[kMaxT];
+            float part = 0.f;
+#pragma unroll
+            for (int t = 0; t < kMaxT; ++t) {
+                const float wp = seg_prev<L>(w[t], t > 0 ? w[t - 1] : 0.f, lane);
+                const float wn = seg_next<L>(w[t], t + 1 < kMaxT ? w[t + 1] : 0.f, lane);
+                const int k = t * L + j;
+                c[t] = (k >= 1 && k <= nw) ? (fmaxf(wp, w[t]) + fmaxf(w[t], wn)) * 0.5f + 0.01f + 1e-5f : 0.f;
+                part += c[t];
+            }
+            const float total = seg_sum<L>(part);
+#pragma unroll
+            for (int t = 0; t < kMaxT; ++t) c[t] = c[t] / total;
+            seg_scan<L, kMaxT, false>(c, lane);                     // c[t] = cdf[k], k = 0 .. nw
+            float* const cdf = s_sd;
+#pragma unroll
+            for (int t = 0; t < kMaxT; ++t) {
+                const int k = t * L + j;
+                if (k <= nw) cdf[k] = c[t];
+                if (k < Dc) s_tc[k] = nxt_tc[t];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int t = 0; t < kMaxT; ++t) {
+                const int jf = t * L + j;
+                float tf = 0.f;
+                if (jf < Df && nxt_ok) {
+                    const float u = P.u_fine ? __ldg(P.u_fine + nxt_gr * Df + jf) : hash_uniform(seed ^ 0xA5A5A5A5DEADBEEFull, (uint64_t)(nxt_gr * Df + jf));
+                    int lo = 0, hi = nw + 1;                         // searchsorted(cdf, u, right=True): first index with cdf[idx] > u
+                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (cdf[mid] <= u) lo = mid + 1; else hi = mid; }
+                    const int below = max(lo - 1, 0), above = min(lo, nw);
+                    const float cb = cdf[below], ca = cdf[above];
+                    const float bb = 0.5f * (s_tc[below] + s_tc[below + 1]), ba = 0.5f * (s_tc[above] + s_tc[above + 1]);
+                    float denom = ca - cb;
+                    if (denom < 1e-5f) denom = 1.f;
+                    tf = bb + (u - cb) / denom * (ba - bb);
+                }
+                nxt_tf[t] = tf;
+                if (eset == 0 && jf < Df) sTfine[(r & 1) * kTfineFloats + rs * Df + jf] = tf;
+            }
+            __syncwarp();
+            if (eset == 0 && lane == 0) mbar_arrive(S.bar(BAR_FINE + (r & 1)));
+        };
+
+        // ---- final weights + colour composite of group r (state in cur_*).  use_fine: merge coarse + fine; else coarse only.
+        auto composite = [&](int r, bool use_fine) {
+            const float (&tc)[kMaxT] = cur_tc;
+            const float (&sc)[kMaxT] = cur_sc;
+            const long long gr = cur_gr;
+            const bool ok = cur_ok;
+            const int cnt = use_fine ? Dt : Dc;
+            float coef_c[kMaxT], coef_f[kMaxT];
+            float wsum, dacc;
+            float d_first, d_last;
+            if (use_fine) {
+                // stable sort-merge of coarse (sorted) + fine depths by rank (torch.sort of the concatenation, renderer.py:164-182)
+#pragma unroll
+                for (int t = 0; t < kMaxT; ++t) {
+                    const int k = t * L + j;
+                    if (k < Dc) s_tc[k] = tc[t];
+                    if (k < Df) s_tf[k] = cur_tf[t];
+                    if (k <= Dc) s_hist[k] = 0;
+                }
+                if (j == 0 && L * kMaxT <= Dc) s_hist[Dc] = 0;
+                __syncwarp();
+                int pos_f[kMaxT], pos_c[kMaxT];
+#pragma unroll
+                for (int t = 0; t < kMaxT; ++t) {
+                    const int jf = t * L + j;
+                    pos_f[t] = 0;
+                    if (jf < Df) {
+                        const float v = cur_tf[t];
+                        int lo = 0, hi = Dc;                         // number of coarse samples <= v (coarse depths strictly increase)
+                        while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_tc[mid] <= v) lo = mid + 1; else hi = mid; }
+                        atomicAdd(&s_hist[lo], 1);
+                        int cntf = 0;
+#pragma unroll 4
+                        for (int i = 0; i < Df; ++i) {
+                            const float x = s_tf[i];
+                            cntf += (x < v || (x == v && i < jf)) ? 1 : 0;
+                        }
+                        pos_f[t] = lo + cntf;
+                    }
+                }
+                __syncwarp();
+                // coarse sample a lands after every fine sample with fewer than a+1 coarse samples <= it: a + #{fine: cnt_c <= a}
+                float hc[kMaxT];
+#pragma unroll
+                for (int t = 0; t < kMaxT; ++t) { const int k = t * L + j; hc[t] = k < Dc ? (float)s_hist[k] : 0.f; }
+                seg_scan<L, kMaxT, false>(hc, lane);
+#pragma unroll
+                for (int t = 0; t < kMaxT; ++t) {
+                    const int k = t * L + j;
+                    pos_c[t] = k + (int)hc[t];
+                    if (k < Dc) { s_sd[pos_c[t]] = tc[t]; s_sg[pos_c[t]] = sc[t]; }
+                    if (k < Df) { s_sd[pos_f[t]] = cur_tf[t]; s_sg[pos_f[t]] = cur_sf[t]; }
+                }
+                __syncwarp();
+                float d6[2 * kMaxT], s6[2 * kMaxT], w6[2 * kMaxT], tm6[2 * kMaxT];
+#pragma unroll
+                for (int t = 0; t < 2 * kMaxT; ++t) {
+                    const int p = t * L + j;
+                    d6[t] = p < cnt ? s_sd[p] : 0.f;
+                    s6[t] = p < cnt ? s_sg[p] : 0.f;
+                }
+                march_weights<L, 2 * kMaxT>(d6, s6, cnt, lane, w6, tm6);
+                float ws = 0.f, da = 0.f;
+                if (j == 0) s_wb[0] = 0.f;
+#pragma unroll
+                for (int t = 0; t < 2 * kMaxT; ++t) {
+                    const int p = t * L + j;
+                    if (p < cnt) s_wb[p + 1] = w6[t];
+                    ws += w6[t];
+                    da += w6[t] * tm6[t];
+                }
+                wsum = seg_sum<L>(ws);
+                dacc = seg_sum<L>(da);
+                d_first = __shfl_sync(FULL, d6[0], lane & ~(L - 1));
+                __syncwarp();
+                d_last = s_sd[cnt - 1];
+#pragma unroll
+                for (int t = 0; t < kMaxT; ++t) {
+                    const int k = t * L + j;
+                    coef_c[t] = k < Dc ? 0.5f * (s_wb[pos_c[t]] + s_wb[pos_c[t] + 1]) : 0.f;
+                    coef_f[t] = k < Df ? 0.5f * (s_wb[pos_f[t]] + s_wb[pos_f[t] + 1]) : 0.f;
+                }
+            } else {
+                float w3[kMaxT], tm3[kMaxT];
+                march_weights<L, kMaxT>(tc, sc, cnt, lane, w3, tm3);
+                float ws = 0.f, da = 0.f;
+#pragma unroll
+                for (int t = 0; t < kMaxT; ++t) { ws += w3[t]; da += w3[t] * tm3[t]; }
+                wsum = seg_sum<L>(ws);
+                dacc = seg_sum<L>(da);
+#pragma unroll
+                for (int t = 0; t < kMaxT; ++t) {
+                    const float wp = seg_prev<L>(w3[t], t > 0 ? w3[t - 1] : 0.f, lane);
+                    const int k = t * L + j;
+                    coef_c[t] = k < Dc ? 0.5f * ((k > 0 ? wp : 0.f) + w3[t]) : 0.f;
+                    coef_f[t] = 0.f;
+                }
+                d_first = __shfl_sync(FULL, tc[0], lane & ~(L - 1));
+                if (j == 0) s_wb[0] = 0.f;                          // keep the scratch race-free across phases
+#pragma unroll
+                for (int t = 0; t < kMaxT; ++t) { const int k = t * L + j; if (k < Dc) s_sd[k] = tc[t]; }
+                __syncwarp();
+                d_last = s_sd[Dc - 1];
+            }
+            // colours: acc[c] += coef * (sigmoid(logit + b1) * 1.002 - 0.001) over this thread's rows, channels 16*eset .. +15
+            float acc[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+            const float4* bc4 = reinterpret_cast<const float4*>(sB1c + 16 * eset);
+            auto add_tile = [&](int slot, float coef) {
+                uint32_t v[16];
+                tmem_ld16_nowait(tlane + kColSlot + 32u * slot + 16u * eset, v);
+                tmem_wait_ld();
+                reg_fence16(v);
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    const float4 bb = bc4[c4];
+                    const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float x = __uint_as_float(v[c4 * 4 + e]) + bv[e];
+                        const float col = skip_act ? x : fmaf(sigmoid_fast(x), 1.002f, -0.001f);
+                        acc[c4 * 4 + e] = fmaf(coef, col, acc[c4 * 4 + e]);
+                    }
+                }
+            };
+#pragma unroll
+            for (int t = 0; t < kMaxT; ++t)
+                if (t < Tc) add_tile((r & 1) * 3 + t, coef_c[t]);
+            if (use_fine) {
+#pragma unroll
+                for (int t = 0; t < kMaxT; ++t)
+                    if (t < Tf) add_tile(6 + t, coef_f[t]);
+            }
+            // the colour slots (and the fine slots) of this group may be overwritten from here on
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(S.bar(BAR_CFREE + (r & 1)));
+                if (use_fine) mbar_arrive(S.bar(BAR_FFREE));
+            }
+            // segment reduce-scatter: lane j ends with channel (j & 15) summed over the L lanes
+            if (L == 32) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) acc[c] += __shfl_xor_sync(FULL, acc[c], 16);
+            }
+#pragma unroll
+            for (int h = 8; h >= 1; h >>= 1) {
+                const bool up = (j & h) != 0;
+#pragma unroll
+                for (int c = 0; c < h; ++c) {
+                    const float send = up ? acc[c] : acc[c + h];
+                    const float keep = up ? acc[c + h] : acc[c];
+                    acc[c] = keep + __shfl_xor_sync(FULL, send, h);
+                }
+            }
+            if (ok && j < 16) {
+                float v = acc[0];
+                if (P.white_back) v = v + 1.f - wsum;
+                P.rgb[gr * kFeat + 16 * eset + j] = v * 2.f - 1.f;
+            }
+            if (ok && eset == 0 && j == 0) {
+                float depth = dacc / wsum;
+                if (isnan(depth)) depth = INFINITY;                  // nan_to_num(nan=inf); the clamp kernel finishes the job
+                P.depth[gr] = depth;
+                P.wsum[gr] = wsum;
+                dmin = fminf(dmin, d_first);
+                dmax = fmaxf(dmax, d_last);
+            }
+        };
+
+        // ---- sigma of tile (kind, r, t) arrived: store it; the last tile of a pass triggers the per-ray phases
+        int pend_kind = -1, pend_r = 0, pend_t = 0, pend_i = 0;      // kind: 0 coarse, 1 fine
+        auto epi2 = [&]() {
+            const float sg = read_sigma(pend_i);
+            if (pend_kind == 0) {
+#pragma unroll
+                for (int t = 0; t < kMaxT; ++t) if (t == pend_t) nxt_sc[t] = sg;
+                if (pend_t == Tc - 1) {
+                    // depths + ray of the coarse group
+                    const RayId id = ray_of(K, g_begin + pend_r, rs);
+                    nxt_ok = id.ok; nxt_gr = id.gr;
+#pragma unroll
+                    for (int t = 0; t < kMaxT; ++t) { const int k = t * L + j; nxt_tc[t] = (id.ok && k < Dc) ? coarse_depth(K, seed, id.gr, k) : 0.f; }
+                    if (Tf > 0) {
+                        importance(pend_r);
+                        if (pend_r == 0) {
+#pragma unroll
+                            for (int t = 0; t < kMaxT; ++t) { cur_tc[t] = nxt_tc[t]; cur_sc[t] = nxt_sc[t]; cur_tf[t] = nxt_tf[t]; }
+                            cur_gr = nxt_gr; cur_ok = nxt_ok;
+                        }
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < kMaxT; ++t) { cur_tc[t] = nxt_tc[t]; cur_sc[t] = nxt_sc[t]; }
+                        cur_gr = nxt_gr; cur_ok = nxt_ok;
+                        composite(pend_r, false);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < kMaxT; ++t) if (t == pend_t) cur_sf[t] = sg;
+                if (pend_t == Tf - 1) {
+                    composite(pend_r, true);
+#pragma unroll
+                    for (int t = 0; t < kMaxT; ++t) { cur_tc[t] = nxt_tc[t]; cur_sc[t] = nxt_sc[t]; cur_tf[t] = nxt_tf[t]; }
+                    cur_gr = nxt_gr; cur_ok = nxt_ok;
+                }
+            }
+        };
+
+        int i = 0;
+        for (int r = 0; r <= n_groups; ++r) {
+            if (r < n_groups)
+                for (int t = 0; t < Tc; ++t) {
+                    epi1(i);
+                    if (pend_kind >= 0) epi2();
+                    pend_kind = 0; pend_r = r; pend_t = t; pend_i = i;
+                    ++i;
+                }
+            if (r >= 1)
+                for (int t = 0; t < Tf; ++t) {
+                    // a fine tile directly behind the coarse tiles of its own group (single-group CTA): its depths come out of
+                    // the pending coarse epilogue, which therefore cannot be deferred behind this tile's layer-1 epilogue
+                    if (pend_kind == 0 && pend_r == r - 1) { epi2(); pend_kind = -1; }
+                    epi1(i);
+                    if (pend_kind >= 0) epi2();
+                    pend_kind = 1; pend_r = r - 1; pend_t = t; pend_i = i;
+                    ++i;
+                }
+        }
+        if (pend_kind >= 0) epi2();
+
+        // batch-global depth range (ray_marcher.py:54): one atomic pair per warp of set 0
+        if (eset == 0 && P.depth_minmax) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                dmin = fminf(dmin, __shfl_xor_sync(FULL, dmin, o));
+                dmax = fmaxf(dmax, __shfl_xor_sync(FULL, dmax, o));
+            }
+            if (lane == 0) {       // depths are positive (ray_start > 0): IEEE ordering == signed-int ordering
+                if (dmin < INFINITY) atomicMin(reinterpret_cast<int*>(P.depth_minmax), __float_as_int(dmin));
+                if (dmax > -INFINITY) atomicMax(reinterpret_cast<int*>(P.depth_minmax) + 1, __float_as_int(dmax));
+            }
+        }
+    }
+
+    // ---- teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kWarps - 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    }
+}
+
+struct DeviceInfo {
+    bool configured16 = false, configured32 = false;
+    int num_sms = 0;
+};
+DeviceInfo g_dev[64];
+
+}  // namespace
+
+int n3d_render_fused_launch(const N3DRender* p, void* stream, int mode) {
+    const int dmaxv = p->depth_coarse > p->depth_fine ? p->depth_coarse : p->depth_fine;
+    const int L = dmaxv <= 48 ? 16 : 32;
+    FusedK K;
+    K.p = *p;
+    K.M = p->res * p->res;
+    K.delta_coarse = (float)(((double)p->ray_end - (double)p->ray_start) / (double)(p->depth_coarse - 1));
+    K.scale = 2.f / p->box_warp;
+    K.Tc = (p->depth_coarse + L - 1) / L;
+    K.Tf = (p->depth_fine + L - 1) / L;
+    K.gw = L == 16 ? 4 : 2;
+    K.log2gw = L == 16 ? 2 : 1;
+    const int tiles_x = (p->res + K.gw - 1) / K.gw, tiles_y = (p->res + 1) / 2;
+    K.blocks_x = (tiles_x + 3) / 4;
+    const int blocks_y = (tiles_y + 7) / 8;
+    K.gpi = K.blocks_x * blocks_y * 32;
+    K.total_groups = (long long)p->N * K.gpi;
+    K.mode = mode;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+        n3d_set_error("n3d_render_rays: cannot query the current device");
+        return N3D_ERR_CUDA;
+    }
+    DeviceInfo& D = g_dev[dev];
+    const size_t smem = (size_t)kSmemBytes + 1024;
+    if (!D.num_sms) {
+        cudaDeviceGetAttribute(&D.num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (D.num_sms <= 0) D.num_sms = 148;
+    }
+    bool& configured = L == 16 ? D.configured16 : D.configured32;
+    if (!configured) {
+        const cudaError_t e = L == 16 ? cudaFuncSetAttribute(render_fused_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                      : cudaFuncSetAttribute(render_fused_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            n3d_set_error("n3d_render_rays: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
+            return N3D_ERR_CUDA;
+        }
+        configured = true;
+    }
+    const int grid = (int)(K.total_groups < D.num_sms ? K.total_groups : D.num_sms);
+    if (L == 16) render_fused_kernel<16><<<grid, kThreads, smem, (cudaStream_t)stream>>>(K);
+    else render_fused_kernel<32><<<grid, kThreads, smem, (cudaStream_t)stream>>>(K);
+    N3D_CHECK_LAUNCH("n3d_render_rays");
+    return N3D_OK;
+}

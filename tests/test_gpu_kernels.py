@@ -398,19 +398,22 @@ def test_blend(K):
 
 
 # ------------------------------------------------------------------------------------------------ renderer
-@pytest.mark.parametrize('N,res,D', [(2, 32, 48), (1, 16, 96), (1, 24, 36)])
-def test_render_rays(K, N, res, D):
+@pytest.mark.parametrize('N,res,D,Df', [(2, 32, 48, 48), (1, 16, 96, 96), (1, 24, 36, 36), (1, 20, 48, 0), (1, 16, 40, 24), (2, 12, 12, 70),
+                                        (3, 64, 48, 48)])
+def test_render_rays(K, N, res, D, Df):
+    """Fused renderer vs the oracle with injected sampler noise: both lane layouts (<= 48 / <= 96 samples per pass), ragged tiles,
+    image sizes that are not a multiple of the pixel block, coarse-only rendering and unequal coarse / fine resolutions."""
     from next3d_b200 import config, weights
     from oracle import renderer as orr
     cfg = config.tiny_config()
-    opts = dict(cfg.rendering_kwargs, depth_resolution=D, depth_resolution_importance=D)
+    opts = dict(cfg.rendering_kwargs, depth_resolution=D, depth_resolution_importance=Df)
     g = _g(47 + res)
     planes = torch.randn(N, 3, 32, 64, 64, generator=g)
     sd = {'decoder.net.0.weight': torch.randn(64, 32, generator=g), 'decoder.net.0.bias': torch.randn(64, generator=g) * 0.1,
           'decoder.net.2.weight': torch.randn(33, 64, generator=g), 'decoder.net.2.bias': torch.randn(33, generator=g) * 0.1}
     _, _, c, _ = weights.demo_inputs(cfg, N, seed=5)
     u_c = torch.rand(N, res * res, D, 1, generator=g)
-    u_f = torch.rand(N * res * res, D, generator=g)
+    u_f = torch.rand(N * res * res, max(Df, 1), generator=g)
     cam, intr = c[:, :16].reshape(-1, 4, 4), c[:, 16:25].reshape(-1, 3, 3)
     o, d = orr.ray_sampler(cam, intr, res)
     rgb_ref, depth_ref, w_ref = orr.render(sd, planes, o, d, opts, u_c, u_f)
