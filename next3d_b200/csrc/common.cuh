@@ -68,6 +68,13 @@ __device__ __forceinline__ void ld_global_256(const float* p, float* v) {
                  : "memory");
 }
 
+// read-only variant (non-coherent path, freely schedulable: no volatile, no memory clobber)
+__device__ __forceinline__ void ldg_nc_256(const float* p, float* v) {
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+        : "l"(p));
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
     return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }

@@ -42,8 +42,9 @@ constexpr uint32_t kColL1 = 0, kColH = 64, kColSig = 192, kColSlot = 224;
 
 // shared-memory byte offsets (base 1024-aligned)
 constexpr int kOffW0hi = 0, kOffW0lo = 4096, kOffWchi = 8192, kOffWclo = 12288, kOffWshi = 16384, kOffWslo = 18432;
-constexpr int kOffF = 20480;                                    // 2 x (hi 8 KiB | lo 8 KiB)
-constexpr int kOffTaps = kOffF + 2 * 16384;                     // 8 warps x [12][32] x (offset, weight)
+constexpr int kNF = 3;                                          // layer-1 A-operand buffers
+constexpr int kOffF = 20480;                                    // kNF x (hi 8 KiB | lo 8 KiB)
+constexpr int kOffTaps = kOffF + kNF * 16384;                     // 8 warps x [12][32] x (offset, weight)
 constexpr int kTapBytesPerWarp = 12 * 32 * 8;
 constexpr int kOffEscr = kOffTaps + kGWarps * kTapBytesPerWarp; // per-E-warp scratch
 constexpr int kEscrFloats = 896;
@@ -51,11 +52,11 @@ constexpr int kOffTfine = kOffEscr + kEWarps * kEscrFloats * 4; // [2][rays per 
 constexpr int kTfineFloats = 384;
 constexpr int kOffBias = kOffTfine + 2 * kTfineFloats * 4;      // b0 * log2e [64] | b1 colour [32] | b1 sigma [1] (+pad)
 constexpr int kOffBar = kOffBias + (64 + 32 + 16) * 4;
-constexpr int kNumBars = 16;
+constexpr int kNumBars = 20;
 constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16;
 
-enum { BAR_FFULL = 0, BAR_FEMPTY = 2, BAR_L1DONE = 4, BAR_L1FREE = 5, BAR_HFULL = 6, BAR_L2DONE = 8, BAR_CFREE = 10, BAR_FFREE = 12,
-       BAR_FINE = 13 };
+enum { BAR_FFULL = 0, BAR_FEMPTY = 3, BAR_L1DONE = 6, BAR_L1FREE = 7, BAR_HFULL = 8, BAR_L2DONE = 10, BAR_CFREE = 12, BAR_FFREE = 14,
+       BAR_FINE = 15 };
 
 struct FusedK {
     N3DRender p;
@@ -65,7 +66,7 @@ struct FusedK {
     int gw, log2gw;              // pixel block of a group: gw x 2
     int blocks_x, gpi;           // group map: blocks of 4 x 8 groups, groups per image (padded)
     long long total_groups;
-    int mode;                    // diagnostics: bit 0 = skip the plane loads (gather floor off), bit 1 = skip activations
+    int mode;                    // diagnostics: bit 0 = all taps read texel 0 (no cache misses)
 };
 
 // ---------------------------------------------------------------------------------------------------------------- group -> rays
@@ -74,10 +75,10 @@ struct RayId {
     bool ok;
     long long gr;
 };
-__device__ __forceinline__ RayId ray_of(const FusedK& K, long long gg, int rs) {
+__device__ __forceinline__ RayId ray_of(const FusedK& K, int gg, int rs) {
     RayId r;
-    const int n = (int)(gg / K.gpi);
-    const int q = (int)(gg - (long long)n * K.gpi);
+    const int n = gg / K.gpi;
+    const int q = gg - n * K.gpi;
     const int blk = q >> 5, inb = q & 31;
     const int byi = blk / K.blocks_x, bxi = blk - byi * K.blocks_x;
     const int tx = bxi * 4 + (inb & 3), ty = byi * 8 + (inb >> 2);
@@ -96,13 +97,13 @@ struct Ray {
     bool ok;
 };
 // ray_sampler.py:43-63 for pixel (row i, column j)
-__device__ __forceinline__ Ray make_ray(const FusedK& K, long long gg, int rs) {
+__device__ __forceinline__ Ray make_ray(const FusedK& K, int gg, int rs) {
     const N3DRender& P = K.p;
     const RayId id = ray_of(K, gg, rs);
     Ray r;
     r.ok = id.ok;
     r.gr = id.gr;
-    r.img4 = (uint32_t)id.n * (uint32_t)(3 * P.PH * P.PW * 8);
+    r.img4 = (uint32_t)id.n * (uint32_t)(3 * P.PH * P.PW * 128);       // byte offset of the image's planes
     r.ox = r.oy = r.oz = r.dx = r.dy = r.dz = 0.f;
     if (id.ok) {
         const float inv = 1.f / (float)P.res, half = 0.5f / (float)P.res;
@@ -134,7 +135,7 @@ __device__ __forceinline__ float coarse_depth(const FusedK& K, uint64_t seed, lo
 
 // ---------------------------------------------------------------------------------------------------------------- gather warps
 // 12 bilinear taps of one sample (3 planes x 4 corners; plane 0 <- (x,y), 1 <- (x,z), 2 <- (z,y); grid_sample zeros padding,
-// align_corners=False): float4-index of the texel's first channel group + weight.  Zero-weight taps all point at texel 0.
+// align_corners=False): byte offset of the texel + weight / 3.  Zero-weight taps all point at texel 0.
 __device__ __forceinline__ void setup_taps(uint2* __restrict__ taps, int lane, float px, float py, float pz, bool valid, uint32_t img4, int PH,
                                            int PW, float scale) {
     const float x = scale * px, y = scale * py, z = scale * pz;
@@ -145,59 +146,56 @@ __device__ __forceinline__ void setup_taps(uint2* __restrict__ taps, int lane, f
         const float flx = floorf(ix), fly = floorf(iy);
         const float fx = ix - flx, fy = iy - fly;
         const int x0 = (int)fminf(fmaxf(flx, -2.f), (float)PW), y0 = (int)fminf(fmaxf(fly, -2.f), (float)PH);
-        const uint32_t pbase = img4 + (uint32_t)(pl * PH * PW) * 8u;
+        const uint32_t pbase = img4 + (uint32_t)(pl * PH * PW) * 128u;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const int xi = x0 + (c & 1), yi = y0 + (c >> 1);
             const float wx = (c & 1) ? fx : 1.f - fx, wy = (c >> 1) ? fy : 1.f - fy;
             const bool inside = valid && xi >= 0 && xi < PW && yi >= 0 && yi < PH;
-            const float w = inside ? wx * wy : 0.f;
-            const uint32_t off = inside ? pbase + (uint32_t)(yi * PW + xi) * 8u : 0u;
+            const float w = inside ? wx * wy * (1.f / 3.f) : 0.f;            // 1/3: mean over the three planes
+            const uint32_t off = inside ? pbase + (uint32_t)(yi * PW + xi) * 128u : 0u;
             taps[(pl * 4 + c) * 32 + lane] = make_uint2(off, __float_as_uint(w));
         }
     }
 }
 
-// 32 samples whose taps sit in `taps`: lanes = 4 samples x 8 channel groups per step; the mean feature goes straight into the
-// K-major SWIZZLE_64B bf16 (hi, lo) A-operand tile rows row0..row0+31.
-__device__ __forceinline__ void gather_rows(const float4* __restrict__ planes4, const uint2* __restrict__ taps, uint8_t* __restrict__ f_hi,
-                                            uint8_t* __restrict__ f_lo, int row0, int lane, bool skip_loads) {
-    const int c4 = lane & 7;
+// 32 samples whose taps sit in `taps`: lanes = 8 samples x 4 channel octets per step (4 steps); every tap is one 256-bit load per
+// lane (four lanes cover the texel's 128-byte line), accumulated with packed fp32x2 FMAs; the mean feature goes straight into the
+// K-major SWIZZLE_64B bf16 (hi, lo) A-operand tile rows row0..row0+31 as one 16-byte store per lane and operand half.
+// Weights already carry the 1/3 of the plane mean.
+__device__ __forceinline__ void gather_rows(const float* __restrict__ planes, const uint2* __restrict__ taps, uint8_t* __restrict__ f_hi,
+                                            uint8_t* __restrict__ f_lo, int row0, int lane) {
+    const int c8 = lane & 3, s8 = lane >> 2;
+    const char* const base = reinterpret_cast<const char*>(planes) + c8 * 32;
+    const uint2* const tl = taps + s8;                          // + tap * 32 + step * 8
 #pragma unroll 1
-    for (int it = 0; it < 8; ++it) {
-        const int s = it * 4 + (lane >> 3);
-        uint2 tp[12];
-        float4 v[12];
+    for (int step = 0; step < 4; ++step) {
+        float2 acc[4];
 #pragma unroll
-        for (int i = 0; i < 12; ++i) tp[i] = taps[i * 32 + s];
-        if (!skip_loads) {
+        for (int half = 0; half < 2; ++half) {
+            uint2 tp[6];
+            float v[6][8];
 #pragma unroll
-            for (int i = 0; i < 12; ++i) v[i] = __ldg(planes4 + tp[i].x + c4);
-        } else {
+            for (int i = 0; i < 6; ++i) tp[i] = tl[(half * 6 + i) * 32 + step * 8];
 #pragma unroll
-            for (int i = 0; i < 12; ++i) v[i] = make_float4(__uint_as_float(tp[i].x), 1.f, 2.f, 3.f);
-        }
-        float4 a[3];
+            for (int i = 0; i < 6; ++i) ldg_nc_256(reinterpret_cast<const float*>(base + tp[i].x), v[i]);
 #pragma unroll
-        for (int pl = 0; pl < 3; ++pl) {
-            float w = __uint_as_float(tp[pl * 4].y);
-            a[pl] = make_float4(w * v[pl * 4].x, w * v[pl * 4].y, w * v[pl * 4].z, w * v[pl * 4].w);
+            for (int i = 0; i < 6; ++i) {
+                const float wt = __uint_as_float(tp[i].y);
+                const float2 w2 = make_float2(wt, wt);
 #pragma unroll
-            for (int c = 1; c < 4; ++c) {
-                w = __uint_as_float(tp[pl * 4 + c].y);
-                const float4 t = v[pl * 4 + c];
-                a[pl].x = fmaf(w, t.x, a[pl].x); a[pl].y = fmaf(w, t.y, a[pl].y); a[pl].z = fmaf(w, t.z, a[pl].z); a[pl].w = fmaf(w, t.w, a[pl].w);
+                for (int c = 0; c < 4; ++c) {
+                    const float2 x = make_float2(v[i][2 * c], v[i][2 * c + 1]);
+                    acc[c] = (half == 0 && i == 0) ? __fmul2_rn(w2, x) : __ffma2_rn(w2, x, acc[c]);
+                }
             }
         }
-        const float third = 1.f / 3.f;
-        const float f0 = ((a[0].x + a[1].x) + a[2].x) * third, f1 = ((a[0].y + a[1].y) + a[2].y) * third;
-        const float f2 = ((a[0].z + a[1].z) + a[2].z) * third, f3 = ((a[0].w + a[1].w) + a[2].w) * third;
-        uint32_t h0, l0, h1, l1;
-        split_bf16x2(f0, f1, h0, l0);
-        split_bf16x2(f2, f3, h1, l1);
-        const uint32_t off = sw64_off(row0 + s, c4 * 8);
-        *reinterpret_cast<uint2*>(f_hi + off) = make_uint2(h0, h1);
-        *reinterpret_cast<uint2*>(f_lo + off) = make_uint2(l0, l1);
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) split_bf16x2(acc[c].x, acc[c].y, h[c], l[c]);
+        const uint32_t off = sw64_off(row0 + step * 8 + s8, c8 * 16);
+        *reinterpret_cast<uint4*>(f_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(f_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
     }
 }
 
@@ -269,6 +267,26 @@ __device__ __forceinline__ void march_weights(const float (&d)[NT], const float 
     }
 }
 
+// Tile stream of a CTA with n groups: C(0) | C(1) F(0) | ... | C(n-1) F(n-2) | F(n-1); every role walks it with the same iterator.
+struct TileIter {
+    int n, Tc, Tf;
+    int r, kind, t;                 // round, 0 coarse / 1 fine, tile of the pass
+    __device__ __forceinline__ TileIter(int n_, int Tc_, int Tf_) : n(n_), Tc(Tc_), Tf(Tf_), r(0), kind(0), t(-1) {}
+    __device__ __forceinline__ bool next() {
+        ++t;
+        for (;;) {
+            if (kind == 0) {
+                if (r < n && t < Tc) return true;
+                kind = 1; t = 0;
+            }
+            if (r >= 1 && t < Tf) return true;
+            kind = 0; t = 0; ++r;
+            if (r > n) return false;
+        }
+    }
+    __device__ __forceinline__ int group() const { return kind == 0 ? r : r - 1; }
+};
+
 struct Smem {
     uint8_t* base;
     __device__ __forceinline__ uint32_t bar(int i) const { return smem_u32(base + kOffBar + i * 8); }
@@ -281,7 +299,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_fused_kernel(const __grid_
     constexpr int RPW = 32 / L;                 // rays per warp
     const N3DRender& P = K.p;
     Smem S;
-    S.base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    S.base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);       // pointer arithmetic keeps the shared address space
     uint8_t* const sb = S.base;
     float* const sB0 = reinterpret_cast<float*>(sb + kOffBias);         // b0 * log2(e)
     float* const sB1c = sB0 + 64;                                        // colour biases (outputs 1..32)
@@ -295,13 +313,12 @@ __global__ void __launch_bounds__(kThreads, 1) render_fused_kernel(const __grid_
     const uint64_t seed = P.seed_ptr ? (P.seed + __ldg(reinterpret_cast<const unsigned long long*>(P.seed_ptr))) : P.seed;
 
     // this CTA's contiguous chunk of groups
-    const long long g_begin = (K.total_groups * blockIdx.x) / gridDim.x;
-    const int n_groups = (int)((K.total_groups * (blockIdx.x + 1)) / gridDim.x - g_begin);
+    const int g_begin = (int)((K.total_groups * blockIdx.x) / gridDim.x);
+    const int n_groups = (int)((K.total_groups * (blockIdx.x + 1)) / gridDim.x) - g_begin;
 
     // ---- one-time setup
     if (tid == 0) {
-        mbar_init(S.bar(BAR_FFULL + 0), 4); mbar_init(S.bar(BAR_FFULL + 1), 4);
-        mbar_init(S.bar(BAR_FEMPTY + 0), 1); mbar_init(S.bar(BAR_FEMPTY + 1), 1);
+        for (int b = 0; b < kNF; ++b) { mbar_init(S.bar(BAR_FFULL + b), 4); mbar_init(S.bar(BAR_FEMPTY + b), 1); }
         mbar_init(S.bar(BAR_L1DONE), 1);
         mbar_init(S.bar(BAR_L1FREE), kEWarps);
         mbar_init(S.bar(BAR_HFULL + 0), kEWarps); mbar_init(S.bar(BAR_HFULL + 1), kEWarps);
@@ -318,26 +335,26 @@ __global__ void __launch_bounds__(kThreads, 1) render_fused_kernel(const __grid_
     for (int i = tid; i < kHidden * kFeat; i += kThreads) {               // W0 [64][32]: row = hidden unit, K = 32 (SWIZZLE_64B)
         const int n = i / kFeat, k = i - n * kFeat;
         __nv_bfloat16 h, l;
-        split_bf16(__ldg(P.w0 + i), h, l);
+        split_bf16(__ldg(P.w0 + i) * kLog2e, h, l);        // layer 1 produces x * log2(e) (the argument of ex2)
         *reinterpret_cast<__nv_bfloat16*>(sb + kOffW0hi + sw64_off(n, k * 2)) = h;
         *reinterpret_cast<__nv_bfloat16*>(sb + kOffW0lo + sw64_off(n, k * 2)) = l;
     }
     for (int i = tid; i < 32 * kHidden; i += kThreads) {                  // colour rows of W1 (outputs 1..32) [32][64] (SWIZZLE_128B)
         const int n = i / kHidden, k = i - n * kHidden;
         __nv_bfloat16 h, l;
-        split_bf16(__ldg(P.w1 + (n + 1) * kHidden + k), h, l);
+        split_bf16(-__ldg(P.w1 + (n + 1) * kHidden + k), h, l);   // hidden units are kept as softplus / ln2; colour logits as -x * log2(e)
         *reinterpret_cast<__nv_bfloat16*>(sb + kOffWchi + sw128_off(n, k * 2)) = h;
         *reinterpret_cast<__nv_bfloat16*>(sb + kOffWclo + sw128_off(n, k * 2)) = l;
     }
     for (int i = tid; i < 16 * kHidden; i += kThreads) {                  // sigma row of W1 (output 0) padded to N = 16
         const int n = i / kHidden, k = i - n * kHidden;
         __nv_bfloat16 h, l;
-        split_bf16(n == 0 ? __ldg(P.w1 + k) : 0.f, h, l);
+        split_bf16(n == 0 ? __ldg(P.w1 + k) * kLn2 : 0.f, h, l);
         *reinterpret_cast<__nv_bfloat16*>(sb + kOffWshi + sw128_off(n, k * 2)) = h;
         *reinterpret_cast<__nv_bfloat16*>(sb + kOffWslo + sw128_off(n, k * 2)) = l;
     }
     for (int i = tid; i < kHidden; i += kThreads) sB0[i] = __ldg(P.b0 + i) * kLog2e;
-    for (int i = tid; i < 32; i += kThreads) sB1c[i] = __ldg(P.b1 + 1 + i);
+    for (int i = tid; i < 32; i += kThreads) sB1c[i] = -kLog2e * __ldg(P.b1 + 1 + i);
     if (tid == 0) sB1s[0] = __ldg(P.b1);
     fence_proxy_async_smem();
     tc_fence_before();
@@ -356,9 +373,9 @@ __global__ void __launch_bounds__(kThreads, 1) render_fused_kernel(const __grid_
             int prev_slot = -1, prev_wait = 0, prev_r = 0;      // prev_wait: 0 none, 1 coarse-slot reuse, 2 fine-slot reuse
             int i = 0;
             auto layer1 = [&](int ti) {
-                const int b = ti & 1;
-                mbar_wait(S.bar(BAR_FFULL + b), (uint32_t)((ti >> 1) & 1), nullptr, 0);
-                if (ti > 0) mbar_wait(S.bar(BAR_L1FREE), (uint32_t)((ti - 1) & 1), nullptr, 0);
+                const int b = ti % kNF;
+                mbar_wait_sleep(S.bar(BAR_FFULL + b), (uint32_t)((ti / kNF) & 1));
+                if (ti > 0) mbar_wait_sleep(S.bar(BAR_L1FREE), (uint32_t)((ti - 1) & 1));
                 tc_fence_after();
                 const uint32_t a_hi = smem_u32(sb + kOffF + b * 16384), a_lo = a_hi + 8192;
 #pragma unroll
@@ -373,9 +390,9 @@ __global__ void __launch_bounds__(kThreads, 1) render_fused_kernel(const __grid_
             };
             auto layer2 = [&](int tj, int slot, int wait_kind, int r) {
                 const int b = tj & 1;
-                mbar_wait(S.bar(BAR_HFULL + b), (uint32_t)((tj >> 1) & 1), nullptr, 0);
-                if (wait_kind == 1) mbar_wait(S.bar(BAR_CFREE + (r & 1)), (uint32_t)(((r >> 1) - 1) & 1), nullptr, 0);
-                if (wait_kind == 2) mbar_wait(S.bar(BAR_FFREE), (uint32_t)((r - 1) & 1), nullptr, 0);
+                mbar_wait_sleep(S.bar(BAR_HFULL + b), (uint32_t)((tj >> 1) & 1));
+                if (wait_kind == 1) mbar_wait_sleep(S.bar(BAR_CFREE + (r & 1)), (uint32_t)(((r >> 1) - 1) & 1));
+                if (wait_kind == 2) mbar_wait_sleep(S.bar(BAR_FFREE), (uint32_t)((r - 1) & 1));
                 tc_fence_after();
                 const uint32_t hA = tmem + kColH + 64u * b;
                 const uint32_t dC = tmem + kColSlot + 32u * slot, dS = tmem + kColSig + 16u * b;
@@ -391,33 +408,28 @@ __global__ void __launch_bounds__(kThreads, 1) render_fused_kernel(const __grid_
                 }
                 umma_commit(S.bar(BAR_L2DONE + b));
             };
-            for (int r = 0; r <= n_groups; ++r) {
-                if (r < n_groups)
-                    for (int t = 0; t < Tc; ++t) {
-                        layer1(i);
-                        if (prev_slot >= 0) layer2(i - 1, prev_slot, prev_wait, prev_r);
-                        prev_slot = (r & 1) * 3 + t; prev_wait = (t == 0 && r >= 2) ? 1 : 0; prev_r = r;
-                        ++i;
-                    }
-                if (r >= 1)
-                    for (int t = 0; t < Tf; ++t) {
-                        // fine tile directly behind its own group's coarse tiles (single-group CTA): the gather of this tile
-                        // waits for the importance sampling, which waits for the previous tile's layer 2
-                        if (prev_slot >= 0 && prev_slot < 6 && prev_r == r - 1) { layer2(i - 1, prev_slot, prev_wait, prev_r); prev_slot = -1; }
-                        layer1(i);
-                        if (prev_slot >= 0) layer2(i - 1, prev_slot, prev_wait, prev_r);
-                        prev_slot = 6 + t; prev_wait = (t == 0 && r - 1 >= 1) ? 2 : 0; prev_r = r - 1;
-                        ++i;
-                    }
+            TileIter it(n_groups, Tc, Tf);
+            for (;;) {
+                const bool has = it.next();
+                const int g = it.group();
+                // a fine tile directly behind its own group's coarse tiles (single-group CTA): the gather of this tile waits for
+                // the importance sampling, which waits for the previous tile's layer 2 -> issue that first
+                const bool early = has && it.kind == 1 && prev_slot >= 0 && prev_slot < 6 && prev_r == g;
+                if (has && !early) layer1(i);
+                if (prev_slot >= 0) layer2(i - 1, prev_slot, prev_wait, prev_r);
+                if (has && early) layer1(i);
+                if (!has) break;
+                prev_slot = it.kind == 0 ? (g & 1) * 3 + it.t : 6 + it.t;
+                prev_wait = it.t != 0 ? 0 : (it.kind == 0 ? (g >= 2 ? 1 : 0) : (g >= 1 ? 2 : 0));
+                prev_r = g;
+                ++i;
             }
-            if (prev_slot >= 0) layer2(i - 1, prev_slot, prev_wait, prev_r);
         }
     }
     // ============================================================================================================ gather warps
     else if (warp >= kEWarps) {
         const int gw = warp - kEWarps;
         uint2* const taps = reinterpret_cast<uint2*>(sb + kOffTaps + gw * kTapBytesPerWarp);
-        const float4* const planes4 = reinterpret_cast<const float4*>(P.planes);
         int next_item = gw;                                   // item = tile * 4 + quarter
         auto item = [&](int ti, int q, bool fine, int r, int t) {
             const int row = q * 32 + lane, rs = row / L, j = row & (L - 1);
@@ -426,16 +438,17 @@ __global__ void __launch_bounds__(kThreads, 1) render_fused_kernel(const __grid_
             const bool valid = ray.ok && k < (fine ? Df : Dc);
             float depth = 0.f;
             if (fine) {
-                mbar_wait(S.bar(BAR_FINE + (r & 1)), (uint32_t)((r >> 1) & 1), nullptr, 0);
+                mbar_wait_sleep(S.bar(BAR_FINE + (r & 1)), (uint32_t)((r >> 1) & 1), 40u);
                 if (valid) depth = sTfine[(r & 1) * kTfineFloats + rs * Df + k];
             } else if (valid) {
                 depth = coarse_depth(K, seed, ray.gr, k);
             }
-            setup_taps(taps, lane, ray.ox + depth * ray.dx, ray.oy + depth * ray.dy, ray.oz + depth * ray.dz, valid, ray.img4, P.PH, P.PW, K.scale);
+            setup_taps(taps, lane, ray.ox + depth * ray.dx, ray.oy + depth * ray.dy, ray.oz + depth * ray.dz, valid && !(K.mode & 1), ray.img4, P.PH, P.PW,
+                       K.scale);
             __syncwarp();
-            const int b = ti & 1;
-            if (ti >= 2) mbar_wait(S.bar(BAR_FEMPTY + b), (uint32_t)(((ti >> 1) - 1) & 1), nullptr, 0);
-            gather_rows(planes4, taps, sb + kOffF + b * 16384, sb + kOffF + b * 16384 + 8192, q * 32, lane, (K.mode & 1) != 0);
+            const int b = ti % kNF;
+            if (ti >= kNF) mbar_wait_sleep(S.bar(BAR_FEMPTY + b), (uint32_t)((ti / kNF - 1) & 1), 40u);
+            gather_rows(P.planes, taps, sb + kOffF + b * 16384, sb + kOffF + b * 16384 + 8192, q * 32, lane);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(S.bar(BAR_FFULL + b));
@@ -446,13 +459,8 @@ __global__ void __launch_bounds__(kThreads, 1) render_fused_kernel(const __grid_
                 next_item += kGWarps;
             }
         };
-        int i = 0;
-        for (int r = 0; r <= n_groups; ++r) {
-            if (r < n_groups)
-                for (int t = 0; t < Tc; ++t, ++i) tile(i, false, r, t);
-            if (r >= 1)
-                for (int t = 0; t < Tf; ++t, ++i) tile(i, true, r - 1, t);
-        }
+        TileIter it(n_groups, Tc, Tf);
+        for (int i = 0; it.next(); ++i) tile(i, it.kind == 1, it.group(), it.t);
     }
     // ============================================================================================================ epilogue warps
     else {
@@ -468,7 +476,6 @@ __global__ void __launch_bounds__(kThreads, 1) render_fused_kernel(const __grid_
         float* const s_tc = es + 3 * RPW * strD + rw * Dc;
         float* const s_tf = es + 3 * RPW * strD + RPW * Dc + rw * Df;
         int* const s_hist = reinterpret_cast<int*>(es + 3 * RPW * strD + RPW * (Dc + Df)) + rw * (Dc + 1);
-        const bool skip_act = (K.mode & 2) != 0;
 
         // state of the group in its fine phase (cur) and of the group in its coarse phase (nxt)
         float cur_tc[kMaxT], cur_sc[kMaxT], cur_tf[kMaxT], cur_sf[kMaxT];
@@ -481,7 +488,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_fused_kernel(const __grid_
 
         // ---- layer-1 epilogue of tile ti: softplus(acc + b0) -> bf16 (hi, lo) words -> hidden buffer (A operand of layer 2)
         auto epi1 = [&](int ti) {
-            mbar_wait(S.bar(BAR_L1DONE), (uint32_t)(ti & 1), nullptr, 0);
+            mbar_wait_sleep(S.bar(BAR_L1DONE), (uint32_t)(ti & 1), 20u);
             tc_fence_after();
             uint32_t a[32];
             tmem_ld16_nowait(tlane + kColL1 + 32u * eset, a);
@@ -492,17 +499,21 @@ __global__ void __launch_bounds__(kThreads, 1) render_fused_kernel(const __grid_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(S.bar(BAR_L1FREE));
+            // hidden unit / ln2 = max(log2(1 + 2^min(y, 126)), y) with y = (x + b0) * log2(e): exact softplus for every finite input
+            // (for y > 24 the sum rounds to 2^y); ln2 is folded into the layer-2 weights
             uint32_t hi[16], lo[16];
             const float4* b4 = reinterpret_cast<const float4*>(sB0 + 32 * eset);
+            float y[32];
 #pragma unroll
             for (int c4 = 0; c4 < 8; ++c4) {
                 const float4 bb = b4[c4];
-                float y0 = fmaf(__uint_as_float(a[c4 * 4]), kLog2e, bb.x), y1 = fmaf(__uint_as_float(a[c4 * 4 + 1]), kLog2e, bb.y);
-                float y2 = fmaf(__uint_as_float(a[c4 * 4 + 2]), kLog2e, bb.z), y3 = fmaf(__uint_as_float(a[c4 * 4 + 3]), kLog2e, bb.w);
-                if (!skip_act) { y0 = softplus_from_log2(y0); y1 = softplus_from_log2(y1); y2 = softplus_from_log2(y2); y3 = softplus_from_log2(y3); }
-                split_bf16x2(y0, y1, hi[c4 * 2], lo[c4 * 2]);
-                split_bf16x2(y2, y3, hi[c4 * 2 + 1], lo[c4 * 2 + 1]);
+                y[c4 * 4] = __uint_as_float(a[c4 * 4]) + bb.x; y[c4 * 4 + 1] = __uint_as_float(a[c4 * 4 + 1]) + bb.y;
+                y[c4 * 4 + 2] = __uint_as_float(a[c4 * 4 + 2]) + bb.z; y[c4 * 4 + 3] = __uint_as_float(a[c4 * 4 + 3]) + bb.w;
             }
+#pragma unroll
+            for (int c = 0; c < 32; ++c) y[c] = fmaxf(lg2_approx(1.f + ex2_approx(fminf(y[c], 126.f))), y[c]);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) split_bf16x2(y[2 * c], y[2 * c + 1], hi[c], lo[c]);
             const uint32_t hb = tlane + kColH + 64u * (ti & 1);
             tmem_st16(hb + 16u * eset, hi);
             tmem_st16(hb + 32u + 16u * eset, lo);
@@ -512,7 +523,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_fused_kernel(const __grid_
             if (lane == 0) mbar_arrive(S.bar(BAR_HFULL + (ti & 1)));
         };
         auto read_sigma = [&](int tj) -> float {
-            mbar_wait(S.bar(BAR_L2DONE + (tj & 1)), (uint32_t)((tj >> 1) & 1), nullptr, 0);
+            mbar_wait_sleep(S.bar(BAR_L2DONE + (tj & 1)), (uint32_t)((tj >> 1) & 1), 20u);
             tc_fence_after();
             uint32_t v;
             tmem_ld1_nowait(tlane + kColSig + 16u * (tj & 1), v);
@@ -675,7 +686,8 @@ __global__ void __launch_bounds__(kThreads, 1) render_fused_kernel(const __grid_
                 __syncwarp();
                 d_last = s_sd[Dc - 1];
             }
-            // colours: acc[c] += coef * (sigmoid(logit + b1) * 1.002 - 0.001) over this thread's rows, channels 16*eset .. +15
+            // colours: acc[c] += coef * sigmoid(logit + b1) over this thread's rows, channels 16*eset .. +15 (sigmoid * 1.002 - 0.001,
+            // triplane_next3d.py:369-370, is affine: applied once to the sum)
             float acc[16];
 #pragma unroll
             for (int c = 0; c < 16; ++c) acc[c] = 0.f;
@@ -685,17 +697,15 @@ __global__ void __launch_bounds__(kThreads, 1) render_fused_kernel(const __grid_
                 tmem_ld16_nowait(tlane + kColSlot + 32u * slot + 16u * eset, v);
                 tmem_wait_ld();
                 reg_fence16(v);
+                float z[16];
 #pragma unroll
                 for (int c4 = 0; c4 < 4; ++c4) {
                     const float4 bb = bc4[c4];
-                    const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float x = __uint_as_float(v[c4 * 4 + e]) + bv[e];
-                        const float col = skip_act ? x : fmaf(sigmoid_fast(x), 1.002f, -0.001f);
-                        acc[c4 * 4 + e] = fmaf(coef, col, acc[c4 * 4 + e]);
-                    }
+                    z[c4 * 4] = __uint_as_float(v[c4 * 4]) + bb.x; z[c4 * 4 + 1] = __uint_as_float(v[c4 * 4 + 1]) + bb.y;
+                    z[c4 * 4 + 2] = __uint_as_float(v[c4 * 4 + 2]) + bb.z; z[c4 * 4 + 3] = __uint_as_float(v[c4 * 4 + 3]) + bb.w;
                 }
+#pragma unroll
+                for (int c = 0; c < 16; ++c) acc[c] = fmaf(coef, rcp_approx(1.f + ex2_approx(z[c])), acc[c]);
             };
 #pragma unroll
             for (int t = 0; t < kMaxT; ++t)
@@ -728,7 +738,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_fused_kernel(const __grid_
                 }
             }
             if (ok && j < 16) {
-                float v = acc[0];
+                float v = fmaf(acc[0], 1.002f, -0.001f * wsum);     // sum_k coef_k (1.002 sigmoid_k - 0.001), sum_k coef_k = wsum
                 if (P.white_back) v = v + 1.f - wsum;
                 P.rgb[gr * kFeat + 16 * eset + j] = v * 2.f - 1.f;
             }
@@ -746,6 +756,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_fused_kernel(const __grid_
         int pend_kind = -1, pend_r = 0, pend_t = 0, pend_i = 0;      // kind: 0 coarse, 1 fine
         auto epi2 = [&]() {
             const float sg = read_sigma(pend_i);
+            bool do_composite = false, shift = false;
             if (pend_kind == 0) {
 #pragma unroll
                 for (int t = 0; t < kMaxT; ++t) if (t == pend_t) nxt_sc[t] = sg;
@@ -757,23 +768,25 @@ __global__ void __launch_bounds__(kThreads, 1) render_fused_kernel(const __grid_
                     for (int t = 0; t < kMaxT; ++t) { const int k = t * L + j; nxt_tc[t] = (id.ok && k < Dc) ? coarse_depth(K, seed, id.gr, k) : 0.f; }
                     if (Tf > 0) {
                         importance(pend_r);
-                        if (pend_r == 0) {
-#pragma unroll
-                            for (int t = 0; t < kMaxT; ++t) { cur_tc[t] = nxt_tc[t]; cur_sc[t] = nxt_sc[t]; cur_tf[t] = nxt_tf[t]; }
-                            cur_gr = nxt_gr; cur_ok = nxt_ok;
-                        }
+                        shift = pend_r == 0;                        // the first group moves to its fine phase right away
                     } else {
-#pragma unroll
-                        for (int t = 0; t < kMaxT; ++t) { cur_tc[t] = nxt_tc[t]; cur_sc[t] = nxt_sc[t]; }
-                        cur_gr = nxt_gr; cur_ok = nxt_ok;
-                        composite(pend_r, false);
+                        shift = true;                               // coarse-only rendering: composite straight from the coarse pass
+                        do_composite = true;
                     }
                 }
             } else {
 #pragma unroll
                 for (int t = 0; t < kMaxT; ++t) if (t == pend_t) cur_sf[t] = sg;
-                if (pend_t == Tf - 1) {
-                    composite(pend_r, true);
+                do_composite = pend_t == Tf - 1;
+            }
+            if (shift) {
+#pragma unroll
+                for (int t = 0; t < kMaxT; ++t) { cur_tc[t] = nxt_tc[t]; cur_sc[t] = nxt_sc[t]; cur_tf[t] = nxt_tf[t]; }
+                cur_gr = nxt_gr; cur_ok = nxt_ok;
+            }
+            if (do_composite) {
+                composite(pend_r, pend_kind == 1);
+                if (pend_kind == 1) {                               // the next group (already importance-sampled) enters its fine phase
 #pragma unroll
                     for (int t = 0; t < kMaxT; ++t) { cur_tc[t] = nxt_tc[t]; cur_sc[t] = nxt_sc[t]; cur_tf[t] = nxt_tf[t]; }
                     cur_gr = nxt_gr; cur_ok = nxt_ok;
@@ -781,27 +794,18 @@ __global__ void __launch_bounds__(kThreads, 1) render_fused_kernel(const __grid_
             }
         };
 
-        int i = 0;
-        for (int r = 0; r <= n_groups; ++r) {
-            if (r < n_groups)
-                for (int t = 0; t < Tc; ++t) {
-                    epi1(i);
-                    if (pend_kind >= 0) epi2();
-                    pend_kind = 0; pend_r = r; pend_t = t; pend_i = i;
-                    ++i;
-                }
-            if (r >= 1)
-                for (int t = 0; t < Tf; ++t) {
-                    // a fine tile directly behind the coarse tiles of its own group (single-group CTA): its depths come out of
-                    // the pending coarse epilogue, which therefore cannot be deferred behind this tile's layer-1 epilogue
-                    if (pend_kind == 0 && pend_r == r - 1) { epi2(); pend_kind = -1; }
-                    epi1(i);
-                    if (pend_kind >= 0) epi2();
-                    pend_kind = 1; pend_r = r - 1; pend_t = t; pend_i = i;
-                    ++i;
-                }
+        TileIter it(n_groups, Tc, Tf);
+        for (int i = 0;; ++i) {
+            const bool has = it.next();
+            // a fine tile directly behind the coarse tiles of its own group (single-group CTA): its depths come out of the pending
+            // coarse epilogue, which therefore cannot be deferred behind this tile's layer-1 epilogue
+            const bool early = has && it.kind == 1 && pend_kind == 0 && pend_r == it.group();
+            if (has && !early) epi1(i);
+            if (pend_kind >= 0) epi2();
+            if (has && early) epi1(i);
+            if (!has) break;
+            pend_kind = it.kind; pend_r = it.group(); pend_t = it.t; pend_i = i;
         }
-        if (pend_kind >= 0) epi2();
 
         // batch-global depth range (ray_marcher.py:54): one atomic pair per warp of set 0
         if (eset == 0 && P.depth_minmax) {

@@ -183,7 +183,7 @@ extern "C" int n3d_render_rays(const N3DRender* p, void* stream) {
     N3D_CHECK_ARG(p->depth_coarse >= 4 && p->depth_fine >= 0, "n3d_render_rays: depth resolutions (%d, %d): need coarse >= 4, fine >= 0",
                   p->depth_coarse, p->depth_fine);
     N3D_CHECK_ARG(p->res >= 1 && p->N >= 1 && p->ray_start > 0.f && p->ray_end > p->ray_start && p->box_warp > 0.f, "n3d_render_rays: bad ray setup");
-    N3D_CHECK_ARG((long long)p->N * 3 * p->PH * p->PW * 8 < (1ll << 32), "n3d_render_rays: plane tensor too large for 32-bit texel offsets");
+    N3D_CHECK_ARG((long long)p->N * 3 * p->PH * p->PW * 128 < (1ll << 32), "n3d_render_rays: plane tensor too large for 32-bit texel offsets");
     static const int mode = getenv("N3D_RENDER_MODE") ? atoi(getenv("N3D_RENDER_MODE")) : 0;      // diagnostics only (phase floors)
     return n3d_render_fused_launch(p, stream, mode);
 }

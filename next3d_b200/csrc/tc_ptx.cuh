@@ -37,6 +37,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
     __trap();
 }
 
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or the hint expires) instead of
+// burning issue slots in a polling loop.  Still bounded: a protocol bug traps.
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, unsigned backoff_ns = 0) {
+#pragma unroll 1
+    for (uint32_t it = 0; it < (1u << 20); ++it) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
+        if (ok) return;
+        if (backoff_ns) __nanosleep(backoff_ns);
+    }
+    __trap();
+}
+
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"

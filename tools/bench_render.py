@@ -1,10 +1,13 @@
-"""Time render_kernel alone on the benchmark workload (planes random, batch 8, 64^2, 48+48).  python tools/bench_render.py"""
+"""Time the fused renderer alone on a benchmark workload (random planes).  python tools/bench_render.py [c2|c3] [modes...]
+modes: N3D_RENDER_MODE values to time in separate processes is not needed -- the mode is read once per process, so run one mode per call."""
 import sys, os, math
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from next3d_b200 import config, weights, kernels as K
 cfg = config.full_config(512)
-N, R = 8, 64
+which = sys.argv[1] if len(sys.argv) > 1 else 'c2'
+N, R, D = (8, 64, 48) if which == 'c2' else (16, 128, 96)
+opts = dict(cfg.rendering_kwargs, depth_resolution=D, depth_resolution_importance=D)
 g = torch.Generator().manual_seed(0)
 planes = torch.randn(N, 3, 256, 256, 32, generator=g).cuda()
 dec = (torch.randn(64, 32, generator=g).cuda() / math.sqrt(32), torch.randn(64, generator=g).cuda() * 0.1,
@@ -13,11 +16,16 @@ _, _, c, _ = weights.demo_inputs(cfg, N)
 cam, intr = c[:, :16].contiguous().cuda(), c[:, 16:25].contiguous().cuda()
 rgb = torch.zeros(N, R * R, 32, device='cuda'); depth = torch.zeros(N, R * R, device='cuda'); wsum = torch.zeros_like(depth)
 mm = torch.tensor([float('inf'), 0.0], device='cuda')
+flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
 for _ in range(3):
-    K.render_rays(planes, cam, intr, R, cfg.rendering_kwargs, dec, rgb, depth, wsum, mm, seed=1)
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
+    K.render_rays(planes, cam, intr, R, opts, dec, rgb, depth, wsum, mm, seed=1)
+ts = []
 for i in range(10):
-    K.render_rays(planes, cam, intr, R, cfg.rendering_kwargs, dec, rgb, depth, wsum, mm, seed=i)
-e1.record(); torch.cuda.synchronize()
-print('N3D_RENDER_THREADS', os.environ.get('N3D_RENDER_THREADS', 'default'), 'render_kernel', e0.elapsed_time(e1) / 10, 'ms')
+    flush.zero_()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    K.render_rays(planes, cam, intr, R, opts, dec, rgb, depth, wsum, mm, seed=i)
+    e1.record(); torch.cuda.synchronize()
+    ts.append(e0.elapsed_time(e1))
+ts.sort()
+print(which, 'N3D_RENDER_MODE', os.environ.get('N3D_RENDER_MODE', '0'), 'render_fused_kernel median', ts[len(ts) // 2], 'ms  min', ts[0], 'ms', flush=True)
