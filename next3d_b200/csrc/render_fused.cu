@@ -47,7 +47,7 @@ constexpr int kOffF = 20480;                                    // kNF x (hi 8 K
 constexpr int kOffTaps = kOffF + kNF * 16384;                     // 8 warps x [12][32] x (offset, weight)
 constexpr int kTapBytesPerWarp = 12 * 32 * 8;
 constexpr int kOffEscr = kOffTaps + kGWarps * kTapBytesPerWarp; // per-E-warp scratch
-constexpr int kEscrFloats = 896;
+constexpr int kEscrFloats = 960;
 constexpr int kOffTfine = kOffEscr + kEWarps * kEscrFloats * 4; // [2][rays per group][Df] fine depths for the gather warps
 constexpr int kTfineFloats = 384;
 constexpr int kOffBias = kOffTfine + 2 * kTfineFloats * 4;      // b0 * log2e [64] | b1 colour [32] | b1 sigma [1] (+pad)
@@ -468,18 +468,22 @@ __global__ void __launch_bounds__(kThreads, 1) render_fused_kernel(const __grid_
         const int row = q * 32 + lane, rs = row / L, j = row & (L - 1), rw = lane / L;
         const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
         float* const es = reinterpret_cast<float*>(sb + kOffEscr) + warp * kEscrFloats;
-        // per-warp scratch (floats): sd | sg | wb : RPW x (Dt + 2) each ; tcs : RPW x Dc ; tfs : RPW x Df ; hist : RPW x (Dc + 1)
+        // per-warp scratch (floats): region A [0, 640) = sd | sg | wb (RPW x (Dt + 2) each), aliased by the cdf during importance sampling
+        // and by the u-bucket tables during ranking; tcs at 640 (RPW x Dc), tfs at 736 (RPW x Df), hist at 832 (RPW x (Dc + 1))
+        constexpr int NB = 8 * L;                                   // u-buckets per ray (8 per lane)
         const int strD = Dt + 2;
-        float* const s_sd = es + rw * strD;                         // sorted depths (aliases the cdf during importance sampling)
+        float* const s_sd = es + rw * strD;                         // sorted depths
         float* const s_sg = es + RPW * strD + rw * strD;
         float* const s_wb = es + 2 * RPW * strD + rw * strD;
-        float* const s_tc = es + 3 * RPW * strD + rw * Dc;
-        float* const s_tf = es + 3 * RPW * strD + RPW * Dc + rw * Df;
-        int* const s_hist = reinterpret_cast<int*>(es + 3 * RPW * strD + RPW * (Dc + Df)) + rw * (Dc + 1);
+        int* const s_ub = reinterpret_cast<int*>(es) + rw * 2 * NB; // [NB] count | prefix << 8, then [NB] member indices (4 bytes)
+        float* const s_tc = es + 640 + rw * Dc;
+        float* const s_tf = es + 736 + rw * Df;
+        int* const s_hist = reinterpret_cast<int*>(es + 832) + rw * (Dc + 1);
 
         // state of the group in its fine phase (cur) and of the group in its coarse phase (nxt)
         float cur_tc[kMaxT], cur_sc[kMaxT], cur_tf[kMaxT], cur_sf[kMaxT];
         float nxt_tc[kMaxT], nxt_sc[kMaxT], nxt_tf[kMaxT];
+        int cur_pk[kMaxT] = {0, 0, 0}, nxt_pk[kMaxT] = {0, 0, 0};     // per fine sample: u-bucket | cdf bin << 16
         long long cur_gr = 0, nxt_gr = 0;
         bool cur_ok = false, nxt_ok = false;
 #pragma unroll
@@ -560,22 +564,38 @@ __global__ void __launch_bounds__(kThreads, 1) render_fused_kernel(const __grid_
                 if (k < Dc) s_tc[k] = nxt_tc[t];
             }
             __syncwarp();
+            float uu[kMaxT];
+            int lo[kMaxT], hi[kMaxT];
+#pragma unroll
+            for (int t = 0; t < kMaxT; ++t) {
+                const int jf = t * L + j;
+                const bool act = jf < Df && nxt_ok;
+                uu[t] = !act ? 0.f : P.u_fine ? __ldg(P.u_fine + nxt_gr * Df + jf) : hash_uniform(seed ^ 0xA5A5A5A5DEADBEEFull, (uint64_t)(nxt_gr * Df + jf));
+                lo[t] = 0;
+                hi[t] = act ? nw + 1 : 0;                            // searchsorted(cdf, u, right=True): first index with cdf[idx] > u
+            }
+            const int nit = 32 - __clz(nw + 1);
+            for (int it = 0; it < nit; ++it) {                       // the three searches of a lane advance together (independent chains)
+#pragma unroll
+                for (int t = 0; t < kMaxT; ++t)
+                    if (lo[t] < hi[t]) { const int mid = (lo[t] + hi[t]) >> 1; if (cdf[mid] <= uu[t]) lo[t] = mid + 1; else hi[t] = mid; }
+            }
 #pragma unroll
             for (int t = 0; t < kMaxT; ++t) {
                 const int jf = t * L + j;
                 float tf = 0.f;
+                int below = 0;
                 if (jf < Df && nxt_ok) {
-                    const float u = P.u_fine ? __ldg(P.u_fine + nxt_gr * Df + jf) : hash_uniform(seed ^ 0xA5A5A5A5DEADBEEFull, (uint64_t)(nxt_gr * Df + jf));
-                    int lo = 0, hi = nw + 1;                         // searchsorted(cdf, u, right=True): first index with cdf[idx] > u
-                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (cdf[mid] <= u) lo = mid + 1; else hi = mid; }
-                    const int below = max(lo - 1, 0), above = min(lo, nw);
+                    below = max(lo[t] - 1, 0);
+                    const int above = min(lo[t], nw);
                     const float cb = cdf[below], ca = cdf[above];
                     const float bb = 0.5f * (s_tc[below] + s_tc[below + 1]), ba = 0.5f * (s_tc[above] + s_tc[above + 1]);
                     float denom = ca - cb;
                     if (denom < 1e-5f) denom = 1.f;
-                    tf = bb + (u - cb) / denom * (ba - bb);
+                    tf = bb + (uu[t] - cb) / denom * (ba - bb);
                 }
                 nxt_tf[t] = tf;
+                nxt_pk[t] = min(NB - 1, (int)(uu[t] * (float)NB)) | (below << 16);
                 if (eset == 0 && jf < Df) sTfine[(r & 1) * kTfineFloats + rs * Df + jf] = tf;
             }
             __syncwarp();
@@ -603,23 +623,79 @@ __global__ void __launch_bounds__(kThreads, 1) render_fused_kernel(const __grid_
                 }
                 if (j == 0 && L * kMaxT <= Dc) s_hist[Dc] = 0;
                 __syncwarp();
-                int pos_f[kMaxT], pos_c[kMaxT];
+                // zero the u-bucket tables (they alias the sorted arrays, which are written after the ranks are known)
+                for (int i = j; i < 2 * NB; i += L) s_ub[i] = 0;
+                __syncwarp();
+                // Rank of a fine sample among the fine ones.  Fine depths are the inverse CDF of iid uniforms u, a monotone map, so the
+                // order of the depths is the order of the u's: bucket the samples by u (NB uniform buckets, ~0.4 samples each), take
+                // the bucket prefix count and order the few members of a bucket by (depth, index).  The number of coarse samples <= v
+                // follows from the CDF bin the sample was drawn from (its depth lies between the midpoints around that bin).
+                int pos_f[kMaxT], pos_c[kMaxT], cntc[kMaxT];
+                bool overflow = false;
+#pragma unroll
+                for (int t = 0; t < kMaxT; ++t) {
+                    const int jf = t * L + j;
+                    cntc[t] = 0;
+                    if (jf < Df) {
+                        const float v = cur_tf[t];
+                        const int key = cur_pk[t] & 0xffff, below = cur_pk[t] >> 16;
+                        const int slot = atomicAdd(&s_ub[key], 1);
+                        if (slot < 4) atomicOr(&s_ub[NB + key], jf << (8 * slot));
+                        int c = below + 1 + (s_tc[below + 1] <= v ? 1 : 0);
+                        if (c == below + 2 && c < Dc && s_tc[c] <= v) ++c;
+                        if (!(s_tc[c - 1] <= v && (c == Dc || s_tc[c] > v))) {       // never taken unless the bracket argument fails: search
+                            int lo = 0, hi = Dc;
+                            while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_tc[mid] <= v) lo = mid + 1; else hi = mid; }
+                            c = lo;
+                        }
+                        cntc[t] = c;
+                        atomicAdd(&s_hist[c], 1);
+                    }
+                }
+                __syncwarp();
+                {   // exclusive prefix over the buckets: lane j owns buckets 8j .. 8j+7; count and prefix share a word
+                    int cn[8], run = 0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { cn[i] = s_ub[8 * j + i]; run += cn[i]; }
+                    int inc = run;
+#pragma unroll
+                    for (int o = 1; o < L; o <<= 1) { const int up = __shfl_up_sync(FULL, inc, o); if (j >= o) inc += up; }
+                    int pre = inc - run;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { s_ub[8 * j + i] = cn[i] | (pre << 8); pre += cn[i]; }
+                }
+                __syncwarp();
 #pragma unroll
                 for (int t = 0; t < kMaxT; ++t) {
                     const int jf = t * L + j;
                     pos_f[t] = 0;
                     if (jf < Df) {
                         const float v = cur_tf[t];
-                        int lo = 0, hi = Dc;                         // number of coarse samples <= v (coarse depths strictly increase)
-                        while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_tc[mid] <= v) lo = mid + 1; else hi = mid; }
-                        atomicAdd(&s_hist[lo], 1);
-                        int cntf = 0;
-#pragma unroll 4
-                        for (int i = 0; i < Df; ++i) {
-                            const float x = s_tf[i];
-                            cntf += (x < v || (x == v && i < jf)) ? 1 : 0;
+                        const int key = cur_pk[t] & 0xffff;
+                        const int word = s_ub[key], cn = word & 255;
+                        const int mem = s_ub[NB + key];
+                        int within = 0;
+                        if (cn > 4) overflow = true;
+                        else {
+#pragma unroll
+                            for (int m = 0; m < 4; ++m) {
+                                const int idx = (mem >> (8 * m)) & 255;
+                                if (m < cn && idx != jf) { const float x = s_tf[idx]; within += (x < v || (x == v && idx < jf)) ? 1 : 0; }
+                            }
                         }
-                        pos_f[t] = lo + cntf;
+                        pos_f[t] = cntc[t] + (word >> 8) + within;
+                    }
+                }
+                if (__any_sync(FULL, overflow)) {                    // a crowded bucket (degenerate u's): full O(Df^2) rank count
+#pragma unroll
+                    for (int t = 0; t < kMaxT; ++t) {
+                        const int jf = t * L + j;
+                        if (jf < Df) {
+                            const float v = cur_tf[t];
+                            int cntf = 0;
+                            for (int i = 0; i < Df; ++i) { const float x = s_tf[i]; cntf += (x < v || (x == v && i < jf)) ? 1 : 0; }
+                            pos_f[t] = cntc[t] + cntf;
+                        }
                     }
                 }
                 __syncwarp();
@@ -781,14 +857,14 @@ __global__ void __launch_bounds__(kThreads, 1) render_fused_kernel(const __grid_
             }
             if (shift) {
 #pragma unroll
-                for (int t = 0; t < kMaxT; ++t) { cur_tc[t] = nxt_tc[t]; cur_sc[t] = nxt_sc[t]; cur_tf[t] = nxt_tf[t]; }
+                for (int t = 0; t < kMaxT; ++t) { cur_tc[t] = nxt_tc[t]; cur_sc[t] = nxt_sc[t]; cur_tf[t] = nxt_tf[t]; cur_pk[t] = nxt_pk[t]; }
                 cur_gr = nxt_gr; cur_ok = nxt_ok;
             }
             if (do_composite) {
                 composite(pend_r, pend_kind == 1);
                 if (pend_kind == 1) {                               // the next group (already importance-sampled) enters its fine phase
 #pragma unroll
-                    for (int t = 0; t < kMaxT; ++t) { cur_tc[t] = nxt_tc[t]; cur_sc[t] = nxt_sc[t]; cur_tf[t] = nxt_tf[t]; }
+                    for (int t = 0; t < kMaxT; ++t) { cur_tc[t] = nxt_tc[t]; cur_sc[t] = nxt_sc[t]; cur_tf[t] = nxt_tf[t]; cur_pk[t] = nxt_pk[t]; }
                     cur_gr = nxt_gr; cur_ok = nxt_ok;
                 }
             }

@@ -398,9 +398,9 @@ def test_blend(K):
 
 
 # ------------------------------------------------------------------------------------------------ renderer
-@pytest.mark.parametrize('N,res,D,Df', [(2, 32, 48, 48), (1, 16, 96, 96), (1, 24, 36, 36), (1, 20, 48, 0), (1, 16, 40, 24), (2, 12, 12, 70),
-                                        (3, 64, 48, 48)])
-def test_render_rays(K, N, res, D, Df):
+@pytest.mark.parametrize('N,res,D,Df,ties', [(2, 32, 48, 48, 0), (1, 16, 96, 96, 0), (1, 24, 36, 36, 0), (1, 20, 48, 0, 0), (1, 16, 40, 24, 0),
+                                             (2, 12, 12, 70, 0), (3, 64, 48, 48, 0), (1, 16, 48, 48, 1), (1, 12, 96, 96, 1)])
+def test_render_rays(K, N, res, D, Df, ties):
     """Fused renderer vs the oracle with injected sampler noise: both lane layouts (<= 48 / <= 96 samples per pass), ragged tiles,
     image sizes that are not a multiple of the pixel block, coarse-only rendering and unequal coarse / fine resolutions."""
     from next3d_b200 import config, weights
@@ -414,6 +414,8 @@ def test_render_rays(K, N, res, D, Df):
     _, _, c, _ = weights.demo_inputs(cfg, N, seed=5)
     u_c = torch.rand(N, res * res, D, 1, generator=g)
     u_f = torch.rand(N * res * res, max(Df, 1), generator=g)
+    if ties:                 # few distinct uniforms: exactly equal fine depths (stable order) and crowded rank buckets (fallback path)
+        u_f = torch.floor(u_f * 5) / 5 + 0.01
     cam, intr = c[:, :16].reshape(-1, 4, 4), c[:, 16:25].reshape(-1, 3, 3)
     o, d = orr.ray_sampler(cam, intr, res)
     rgb_ref, depth_ref, w_ref = orr.render(sd, planes, o, d, opts, u_c, u_f)

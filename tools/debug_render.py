@@ -14,6 +14,7 @@ if len(sys.argv) > 1:
     a = [int(x) for x in sys.argv[1:]]
     cases = [tuple(a[i:i + 4]) for i in range(0, len(a), 4)]
 DEV = 'cuda'
+QUANT = int(os.environ.get('N3D_DEBUG_QUANT', '0'))
 for N, res, D, Df in cases:
     cfg = config.tiny_config()
     opts = dict(cfg.rendering_kwargs, depth_resolution=D, depth_resolution_importance=Df)
@@ -24,6 +25,8 @@ for N, res, D, Df in cases:
     _, _, c, _ = weights.demo_inputs(cfg, N, seed=5)
     u_c = torch.rand(N, res * res, D, 1, generator=g)
     u_f = torch.rand(N * res * res, max(Df, 1), generator=g)
+    if QUANT:
+        u_f = torch.floor(u_f * QUANT) / QUANT + 0.01        # heavy ties and crowded buckets
     cam, intr = c[:, :16].reshape(-1, 4, 4), c[:, 16:25].reshape(-1, 3, 3)
     o, d = orr.ray_sampler(cam, intr, res)
     rgb_ref, depth_ref, w_ref = orr.render(sd, planes, o, d, opts, u_c, u_f)
