@@ -254,6 +254,15 @@ int n3d_sample_points(const float* planes, int N, int PH, int PW, const float* c
                       const float* w0, const float* b0, const float* w1, const float* b1, float* sigma, float* rgb,
                       void* stream);
 
+/* Shape-extraction grid (gen_samples_next3d.py:80-102, 208-238): sigma at the voxel centres of create_samples(N = grid_n,
+ * cube_length) for the flat indices head .. head+count-1, coordinates generated in the kernel with the script's own float32
+ * operations (no [N^3,3] coordinate tensor), written into sigma_grid [grid_n]^3 at the position the script's
+ * flip(dims=[0]) + border trim leaves them; voxels inside the trimmed border (width `pad`, the script's int(30 * N / 256))
+ * receive pad_value and are not decoded.  pad = 0: plain flip.  Planes of ONE sample [3,PH,PW,32]. */
+int n3d_sample_grid(const float* planes, int PH, int PW, int grid_n, float cube_length, float box_warp, int64_t head, int64_t count,
+                    int pad, float pad_value, const float* w0, const float* b0, const float* w1, const float* b1, float* sigma_grid,
+                    void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Host-side input parsers (no device work): what the inference scripts do per frame in Python.
  * ---------------------------------------------------------------------------------------------------------- */

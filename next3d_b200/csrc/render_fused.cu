@@ -292,6 +292,137 @@ struct Smem {
     __device__ __forceinline__ uint32_t bar(int i) const { return smem_u32(base + kOffBar + i * 8); }
 };
 
+// Decoder weights -> bf16 (hi, lo) B-operand tiles in shared memory, with the activation scalings folded in: layer 1 produces
+// x * log2(e); hidden units are kept as softplus / ln2; colour logits as -(x) * log2(e) (the argument of ex2 in the sigmoid).
+__device__ __forceinline__ void stage_decoder(uint8_t* sb, const float* __restrict__ w0, const float* __restrict__ b0, const float* __restrict__ w1,
+                                              const float* __restrict__ b1, int tid) {
+    float* const sB0 = reinterpret_cast<float*>(sb + kOffBias);
+    float* const sB1c = sB0 + 64;
+    float* const sB1s = sB1c + 32;
+    for (int i = tid; i < kHidden * kFeat; i += kThreads) {               // W0 [64][32]: row = hidden unit, K = 32 (SWIZZLE_64B)
+        const int n = i / kFeat, k = i - n * kFeat;
+        __nv_bfloat16 h, l;
+        split_bf16(__ldg(w0 + i) * kLog2e, h, l);        // layer 1 produces x * log2(e) (the argument of ex2)
+        *reinterpret_cast<__nv_bfloat16*>(sb + kOffW0hi + sw64_off(n, k * 2)) = h;
+        *reinterpret_cast<__nv_bfloat16*>(sb + kOffW0lo + sw64_off(n, k * 2)) = l;
+    }
+    for (int i = tid; i < 32 * kHidden; i += kThreads) {                  // colour rows of W1 (outputs 1..32) [32][64] (SWIZZLE_128B)
+        const int n = i / kHidden, k = i - n * kHidden;
+        __nv_bfloat16 h, l;
+        split_bf16(-__ldg(w1 + (n + 1) * kHidden + k), h, l);   // hidden units are kept as softplus / ln2; colour logits as -x * log2(e)
+        *reinterpret_cast<__nv_bfloat16*>(sb + kOffWchi + sw128_off(n, k * 2)) = h;
+        *reinterpret_cast<__nv_bfloat16*>(sb + kOffWclo + sw128_off(n, k * 2)) = l;
+    }
+    for (int i = tid; i < 16 * kHidden; i += kThreads) {                  // sigma row of W1 (output 0) padded to N = 16
+        const int n = i / kHidden, k = i - n * kHidden;
+        __nv_bfloat16 h, l;
+        split_bf16(n == 0 ? __ldg(w1 + k) * kLn2 : 0.f, h, l);
+        *reinterpret_cast<__nv_bfloat16*>(sb + kOffWshi + sw128_off(n, k * 2)) = h;
+        *reinterpret_cast<__nv_bfloat16*>(sb + kOffWslo + sw128_off(n, k * 2)) = l;
+    }
+    for (int i = tid; i < kHidden; i += kThreads) sB0[i] = __ldg(b0 + i) * kLog2e;
+    for (int i = tid; i < 32; i += kThreads) sB1c[i] = -kLog2e * __ldg(b1 + 1 + i);
+    if (tid == 0) sB1s[0] = __ldg(b1);
+}
+
+// layer 1 of tile ti: [128 x 32] x [32 x 64] -> TMEM [kColL1, +64), bf16x3; frees the A buffer and publishes the accumulator
+__device__ __forceinline__ void mma_layer1(const Smem& S, uint32_t tmem, int ti) {
+    uint8_t* const sb = S.base;
+    const uint64_t dhi64 = umma_desc_hi(32);
+    const uint32_t id64 = umma_idesc_bf16(64);
+    const uint32_t w0h = smem_u32(sb + kOffW0hi), w0l = smem_u32(sb + kOffW0lo);
+    const int b = ti % kNF;
+    mbar_wait_sleep(S.bar(BAR_FFULL + b), (uint32_t)((ti / kNF) & 1));
+    if (ti > 0) mbar_wait_sleep(S.bar(BAR_L1FREE), (uint32_t)((ti - 1) & 1));
+    tc_fence_after();
+    const uint32_t a_hi = smem_u32(sb + kOffF + b * 16384), a_lo = a_hi + 8192;
+#pragma unroll
+    for (int k16 = 0; k16 < kFeat / 16; ++k16) {
+        const uint32_t ko = (uint32_t)k16 * 32u;
+        umma_bf16(tmem + kColL1, umma_desc(a_hi + ko, dhi64), umma_desc(w0h + ko, dhi64), id64, k16 != 0);
+        umma_bf16(tmem + kColL1, umma_desc(a_hi + ko, dhi64), umma_desc(w0l + ko, dhi64), id64, 1u);
+        umma_bf16(tmem + kColL1, umma_desc(a_lo + ko, dhi64), umma_desc(w0h + ko, dhi64), id64, 1u);
+    }
+    umma_commit(S.bar(BAR_FEMPTY + b));
+    umma_commit(S.bar(BAR_L1DONE));
+}
+// layer 2 of the tile in hidden buffer b: A from tensor memory; sigma -> [kColSig + 16 b, +16), colour logits -> column col_c
+__device__ __forceinline__ void mma_layer2_issue(const Smem& S, uint32_t tmem, int b, uint32_t col_c, bool colours) {
+    uint8_t* const sb = S.base;
+    const uint64_t dhi128 = umma_desc_hi(64);
+    const uint32_t id32 = umma_idesc_bf16(32), id16 = umma_idesc_bf16(16);
+    const uint32_t wch = smem_u32(sb + kOffWchi), wcl = smem_u32(sb + kOffWclo), wsh = smem_u32(sb + kOffWshi), wsl = smem_u32(sb + kOffWslo);
+    const uint32_t hA = tmem + kColH + 64u * b;
+    const uint32_t dC = tmem + col_c, dS = tmem + kColSig + 16u * b;
+#pragma unroll
+    for (int k16 = 0; k16 < kHidden / 16; ++k16) {
+        const uint32_t ko = (uint32_t)k16 * 32u, ka = (uint32_t)k16 * 8u;
+        if (colours) {
+            umma_bf16_ts(dC, hA + ka, umma_desc(wch + ko, dhi128), id32, k16 != 0);
+            umma_bf16_ts(dC, hA + ka, umma_desc(wcl + ko, dhi128), id32, 1u);
+            umma_bf16_ts(dC, hA + 32u + ka, umma_desc(wch + ko, dhi128), id32, 1u);
+        }
+        umma_bf16_ts(dS, hA + ka, umma_desc(wsh + ko, dhi128), id16, k16 != 0);
+        umma_bf16_ts(dS, hA + ka, umma_desc(wsl + ko, dhi128), id16, 1u);
+        umma_bf16_ts(dS, hA + 32u + ka, umma_desc(wsh + ko, dhi128), id16, 1u);
+    }
+    umma_commit(S.bar(BAR_L2DONE + b));
+}
+// layer-1 epilogue of tile ti (thread = row, this set's 32 hidden units): softplus -> bf16 (hi, lo) words -> hidden buffer
+__device__ __forceinline__ void epi1_tile(const Smem& S, uint32_t tlane, int eset, int lane, int ti) {
+    const float* const sB0 = reinterpret_cast<const float*>(S.base + kOffBias);
+    mbar_wait_sleep(S.bar(BAR_L1DONE), (uint32_t)(ti & 1), 20u);
+    tc_fence_after();
+    uint32_t a[32];
+    tmem_ld16_nowait(tlane + kColL1 + 32u * eset, a);
+    tmem_ld16_nowait(tlane + kColL1 + 32u * eset + 16u, a + 16);
+    tmem_wait_ld();
+    reg_fence16(a);
+    reg_fence16(a + 16);
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(S.bar(BAR_L1FREE));
+    // hidden unit / ln2 = max(log2(1 + 2^min(y, 126)), y) with y = (x + b0) * log2(e): exact softplus for every finite input
+    // (for y > 24 the sum rounds to 2^y); ln2 is folded into the layer-2 weights
+    uint32_t hi[16], lo[16];
+    const float4* b4 = reinterpret_cast<const float4*>(sB0 + 32 * eset);
+    float y[32];
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 bb = b4[c4];
+        y[c4 * 4] = __uint_as_float(a[c4 * 4]) + bb.x; y[c4 * 4 + 1] = __uint_as_float(a[c4 * 4 + 1]) + bb.y;
+        y[c4 * 4 + 2] = __uint_as_float(a[c4 * 4 + 2]) + bb.z; y[c4 * 4 + 3] = __uint_as_float(a[c4 * 4 + 3]) + bb.w;
+    }
+#pragma unroll
+    for (int c = 0; c < 32; ++c) y[c] = fmaxf(lg2_approx(1.f + ex2_approx(fminf(y[c], 126.f))), y[c]);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) split_bf16x2(y[2 * c], y[2 * c + 1], hi[c], lo[c]);
+    const uint32_t hb = tlane + kColH + 64u * (ti & 1);
+    tmem_st16(hb + 16u * eset, hi);
+    tmem_st16(hb + 32u + 16u * eset, lo);
+    tmem_wait_st();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(S.bar(BAR_HFULL + (ti & 1)));
+}
+__device__ __forceinline__ float read_sigma_tile(const Smem& S, uint32_t tlane, int tj) {
+    const float* const sB1s = reinterpret_cast<const float*>(S.base + kOffBias) + 96;
+    mbar_wait_sleep(S.bar(BAR_L2DONE + (tj & 1)), (uint32_t)((tj >> 1) & 1), 20u);
+    tc_fence_after();
+    uint32_t v;
+    tmem_ld1_nowait(tlane + kColSig + 16u * (tj & 1), v);
+    tmem_wait_ld();
+    reg_fence1(v);
+    return __uint_as_float(v) + sB1s[0];
+}
+__device__ __forceinline__ void init_pipeline_barriers(const Smem& S) {
+    for (int b = 0; b < kNF; ++b) { mbar_init(S.bar(BAR_FFULL + b), 4); mbar_init(S.bar(BAR_FEMPTY + b), 1); }
+    mbar_init(S.bar(BAR_L1DONE), 1);
+    mbar_init(S.bar(BAR_L1FREE), kEWarps);
+    mbar_init(S.bar(BAR_HFULL + 0), kEWarps); mbar_init(S.bar(BAR_HFULL + 1), kEWarps);
+    mbar_init(S.bar(BAR_L2DONE + 0), 1); mbar_init(S.bar(BAR_L2DONE + 1), 1);
+}
+
 // ---------------------------------------------------------------------------------------------------------------- the kernel
 template <int L>
 __global__ void __launch_bounds__(kThreads, 1) render_fused_kernel(const __grid_constant__ FusedK K) {
@@ -318,11 +449,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_fused_kernel(const __grid_
 
     // ---- one-time setup
     if (tid == 0) {
-        for (int b = 0; b < kNF; ++b) { mbar_init(S.bar(BAR_FFULL + b), 4); mbar_init(S.bar(BAR_FEMPTY + b), 1); }
-        mbar_init(S.bar(BAR_L1DONE), 1);
-        mbar_init(S.bar(BAR_L1FREE), kEWarps);
-        mbar_init(S.bar(BAR_HFULL + 0), kEWarps); mbar_init(S.bar(BAR_HFULL + 1), kEWarps);
-        mbar_init(S.bar(BAR_L2DONE + 0), 1); mbar_init(S.bar(BAR_L2DONE + 1), 1);
+        init_pipeline_barriers(S);
         mbar_init(S.bar(BAR_CFREE + 0), kEWarps); mbar_init(S.bar(BAR_CFREE + 1), kEWarps);
         mbar_init(S.bar(BAR_FFREE), kEWarps);
         mbar_init(S.bar(BAR_FINE + 0), 4); mbar_init(S.bar(BAR_FINE + 1), 4);
@@ -332,30 +459,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_fused_kernel(const __grid_
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = tid; i < kHidden * kFeat; i += kThreads) {               // W0 [64][32]: row = hidden unit, K = 32 (SWIZZLE_64B)
-        const int n = i / kFeat, k = i - n * kFeat;
-        __nv_bfloat16 h, l;
-        split_bf16(__ldg(P.w0 + i) * kLog2e, h, l);        // layer 1 produces x * log2(e) (the argument of ex2)
-        *reinterpret_cast<__nv_bfloat16*>(sb + kOffW0hi + sw64_off(n, k * 2)) = h;
-        *reinterpret_cast<__nv_bfloat16*>(sb + kOffW0lo + sw64_off(n, k * 2)) = l;
-    }
-    for (int i = tid; i < 32 * kHidden; i += kThreads) {                  // colour rows of W1 (outputs 1..32) [32][64] (SWIZZLE_128B)
-        const int n = i / kHidden, k = i - n * kHidden;
-        __nv_bfloat16 h, l;
-        split_bf16(-__ldg(P.w1 + (n + 1) * kHidden + k), h, l);   // hidden units are kept as softplus / ln2; colour logits as -x * log2(e)
-        *reinterpret_cast<__nv_bfloat16*>(sb + kOffWchi + sw128_off(n, k * 2)) = h;
-        *reinterpret_cast<__nv_bfloat16*>(sb + kOffWclo + sw128_off(n, k * 2)) = l;
-    }
-    for (int i = tid; i < 16 * kHidden; i += kThreads) {                  // sigma row of W1 (output 0) padded to N = 16
-        const int n = i / kHidden, k = i - n * kHidden;
-        __nv_bfloat16 h, l;
-        split_bf16(n == 0 ? __ldg(P.w1 + k) * kLn2 : 0.f, h, l);
-        *reinterpret_cast<__nv_bfloat16*>(sb + kOffWshi + sw128_off(n, k * 2)) = h;
-        *reinterpret_cast<__nv_bfloat16*>(sb + kOffWslo + sw128_off(n, k * 2)) = l;
-    }
-    for (int i = tid; i < kHidden; i += kThreads) sB0[i] = __ldg(P.b0 + i) * kLog2e;
-    for (int i = tid; i < 32; i += kThreads) sB1c[i] = -kLog2e * __ldg(P.b1 + 1 + i);
-    if (tid == 0) sB1s[0] = __ldg(P.b1);
+    stage_decoder(sb, P.w0, P.b0, P.w1, P.b1, tid);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -365,48 +469,17 @@ __global__ void __launch_bounds__(kThreads, 1) render_fused_kernel(const __grid_
     // ============================================================================================================ MMA warp
     if (warp == kWarps - 1) {
         if (lane == 0) {
-            const uint64_t dhi64 = umma_desc_hi(32), dhi128 = umma_desc_hi(64);
-            const uint32_t id64 = umma_idesc_bf16(64), id32 = umma_idesc_bf16(32), id16 = umma_idesc_bf16(16);
-            const uint32_t w0h = smem_u32(sb + kOffW0hi), w0l = smem_u32(sb + kOffW0lo);
-            const uint32_t wch = smem_u32(sb + kOffWchi), wcl = smem_u32(sb + kOffWclo), wsh = smem_u32(sb + kOffWshi), wsl = smem_u32(sb + kOffWslo);
             // slot of the tile before the current one (its layer 2 is issued after the current tile's layer 1)
             int prev_slot = -1, prev_wait = 0, prev_r = 0;      // prev_wait: 0 none, 1 coarse-slot reuse, 2 fine-slot reuse
             int i = 0;
-            auto layer1 = [&](int ti) {
-                const int b = ti % kNF;
-                mbar_wait_sleep(S.bar(BAR_FFULL + b), (uint32_t)((ti / kNF) & 1));
-                if (ti > 0) mbar_wait_sleep(S.bar(BAR_L1FREE), (uint32_t)((ti - 1) & 1));
-                tc_fence_after();
-                const uint32_t a_hi = smem_u32(sb + kOffF + b * 16384), a_lo = a_hi + 8192;
-#pragma unroll
-                for (int k16 = 0; k16 < kFeat / 16; ++k16) {
-                    const uint32_t ko = (uint32_t)k16 * 32u;
-                    umma_bf16(tmem + kColL1, umma_desc(a_hi + ko, dhi64), umma_desc(w0h + ko, dhi64), id64, k16 != 0);
-                    umma_bf16(tmem + kColL1, umma_desc(a_hi + ko, dhi64), umma_desc(w0l + ko, dhi64), id64, 1u);
-                    umma_bf16(tmem + kColL1, umma_desc(a_lo + ko, dhi64), umma_desc(w0h + ko, dhi64), id64, 1u);
-                }
-                umma_commit(S.bar(BAR_FEMPTY + b));
-                umma_commit(S.bar(BAR_L1DONE));
-            };
+            auto layer1 = [&](int ti) { mma_layer1(S, tmem, ti); };
             auto layer2 = [&](int tj, int slot, int wait_kind, int r) {
                 const int b = tj & 1;
                 mbar_wait_sleep(S.bar(BAR_HFULL + b), (uint32_t)((tj >> 1) & 1));
                 if (wait_kind == 1) mbar_wait_sleep(S.bar(BAR_CFREE + (r & 1)), (uint32_t)(((r >> 1) - 1) & 1));
                 if (wait_kind == 2) mbar_wait_sleep(S.bar(BAR_FFREE), (uint32_t)((r - 1) & 1));
                 tc_fence_after();
-                const uint32_t hA = tmem + kColH + 64u * b;
-                const uint32_t dC = tmem + kColSlot + 32u * slot, dS = tmem + kColSig + 16u * b;
-#pragma unroll
-                for (int k16 = 0; k16 < kHidden / 16; ++k16) {
-                    const uint32_t ko = (uint32_t)k16 * 32u, ka = (uint32_t)k16 * 8u;
-                    umma_bf16_ts(dC, hA + ka, umma_desc(wch + ko, dhi128), id32, k16 != 0);
-                    umma_bf16_ts(dC, hA + ka, umma_desc(wcl + ko, dhi128), id32, 1u);
-                    umma_bf16_ts(dC, hA + 32u + ka, umma_desc(wch + ko, dhi128), id32, 1u);
-                    umma_bf16_ts(dS, hA + ka, umma_desc(wsh + ko, dhi128), id16, k16 != 0);
-                    umma_bf16_ts(dS, hA + ka, umma_desc(wsl + ko, dhi128), id16, 1u);
-                    umma_bf16_ts(dS, hA + 32u + ka, umma_desc(wsh + ko, dhi128), id16, 1u);
-                }
-                umma_commit(S.bar(BAR_L2DONE + b));
+                mma_layer2_issue(S, tmem, b, kColSlot + 32u * slot, true);
             };
             TileIter it(n_groups, Tc, Tf);
             for (;;) {
@@ -491,50 +564,8 @@ __global__ void __launch_bounds__(kThreads, 1) render_fused_kernel(const __grid_
         float dmin = INFINITY, dmax = -INFINITY;
 
         // ---- layer-1 epilogue of tile ti: softplus(acc + b0) -> bf16 (hi, lo) words -> hidden buffer (A operand of layer 2)
-        auto epi1 = [&](int ti) {
-            mbar_wait_sleep(S.bar(BAR_L1DONE), (uint32_t)(ti & 1), 20u);
-            tc_fence_after();
-            uint32_t a[32];
-            tmem_ld16_nowait(tlane + kColL1 + 32u * eset, a);
-            tmem_ld16_nowait(tlane + kColL1 + 32u * eset + 16u, a + 16);
-            tmem_wait_ld();
-            reg_fence16(a);
-            reg_fence16(a + 16);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(S.bar(BAR_L1FREE));
-            // hidden unit / ln2 = max(log2(1 + 2^min(y, 126)), y) with y = (x + b0) * log2(e): exact softplus for every finite input
-            // (for y > 24 the sum rounds to 2^y); ln2 is folded into the layer-2 weights
-            uint32_t hi[16], lo[16];
-            const float4* b4 = reinterpret_cast<const float4*>(sB0 + 32 * eset);
-            float y[32];
-#pragma unroll
-            for (int c4 = 0; c4 < 8; ++c4) {
-                const float4 bb = b4[c4];
-                y[c4 * 4] = __uint_as_float(a[c4 * 4]) + bb.x; y[c4 * 4 + 1] = __uint_as_float(a[c4 * 4 + 1]) + bb.y;
-                y[c4 * 4 + 2] = __uint_as_float(a[c4 * 4 + 2]) + bb.z; y[c4 * 4 + 3] = __uint_as_float(a[c4 * 4 + 3]) + bb.w;
-            }
-#pragma unroll
-            for (int c = 0; c < 32; ++c) y[c] = fmaxf(lg2_approx(1.f + ex2_approx(fminf(y[c], 126.f))), y[c]);
-#pragma unroll
-            for (int c = 0; c < 16; ++c) split_bf16x2(y[2 * c], y[2 * c + 1], hi[c], lo[c]);
-            const uint32_t hb = tlane + kColH + 64u * (ti & 1);
-            tmem_st16(hb + 16u * eset, hi);
-            tmem_st16(hb + 32u + 16u * eset, lo);
-            tmem_wait_st();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(S.bar(BAR_HFULL + (ti & 1)));
-        };
-        auto read_sigma = [&](int tj) -> float {
-            mbar_wait_sleep(S.bar(BAR_L2DONE + (tj & 1)), (uint32_t)((tj >> 1) & 1), 20u);
-            tc_fence_after();
-            uint32_t v;
-            tmem_ld1_nowait(tlane + kColSig + 16u * (tj & 1), v);
-            tmem_wait_ld();
-            reg_fence1(v);
-            return __uint_as_float(v) + sB1s[0];
-        };
+        auto epi1 = [&](int ti) { epi1_tile(S, tlane, eset, lane, ti); };
+        auto read_sigma = [&](int tj) -> float { return read_sigma_tile(S, tlane, tj); };
 
         // ---- coarse weights -> smoothed pdf -> cdf -> inverse-CDF fine depths (renderer.py:209-268) for the group in `nxt`
         auto importance = [&](int r) {
@@ -906,8 +937,206 @@ __global__ void __launch_bounds__(kThreads, 1) render_fused_kernel(const __grid_
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------- run_model
+// Decoder on arbitrary points (renderer.run_model, renderer.py:149-155; TriPlaneGenerator.sample, triplane_next3d.py:232-276) with the
+// same gather / tcgen05 / epilogue roles as the renderer, minus the per-ray phases.  Tile = 128 consecutive points.  In grid mode
+// (coords == nullptr) the points are the voxel centres of create_samples (gen_samples_next3d.py:80-102), generated in the kernel
+// with the script's own float32 operations, and the flip + border trim of gen_samples_next3d.py:226-238 is applied on the way
+// out: voxels in the trimmed border get pad_value and are never decoded.
+struct PointsK {
+    const float* planes;
+    int N, PH, PW;
+    const float* coords;         // [N, Pn, 3] or nullptr (grid mode, N = 1)
+    long long Pn, total;         // points per image, N * Pn
+    float scale;
+    const float* w0; const float* b0; const float* w1; const float* b1;
+    float* sigma;                // [N, Pn]  (grid mode: [R, R, R] already flipped + trimmed)
+    float* rgb;                  // [N, Pn, 32] or nullptr
+    int grid_n, pad;             // grid mode: voxels per side, trimmed border width
+    float voxel_size, org0, org1, org2, pad_value;
+    long long head;              // grid mode: flat index of the first point
+};
+
+// voxel centre of flat index idx, bit-identical to the reference's float32 expression chain (float, not floor, division)
+__device__ __forceinline__ void grid_point(const PointsK& K, long long idx, float& x, float& y, float& z) {
+    const float fn = (float)K.grid_n;
+    const float fi = (float)idx;                                   // int64 -> float32, round to nearest (indices above 2^24 lose bits)
+    const float s2 = (float)(idx % K.grid_n);
+    const float q1 = __fdiv_rn(fi, fn);
+    const float s1 = fmodf(q1, fn);
+    const float s0 = fmodf(__fdiv_rn(q1, fn), fn);
+    x = __fadd_rn(__fmul_rn(s0, K.voxel_size), K.org2);
+    y = __fadd_rn(__fmul_rn(s1, K.voxel_size), K.org1);
+    z = __fadd_rn(__fmul_rn(s2, K.voxel_size), K.org0);
+}
+// destination of flat index idx after flip(dims=[0]) and whether it lies in the trimmed border
+__device__ __forceinline__ long long grid_dest(const PointsK& K, long long idx, bool& border) {
+    const long long n = K.grid_n;
+    const long long a = idx / (n * n), rem = idx - a * n * n;
+    const long long b = rem / n, c = rem - b * n;
+    const long long fa = n - 1 - a;
+    border = fa < K.pad || fa >= n - K.pad || b < K.pad || b >= n - K.pad || c < K.pad || c >= n - K.pad;
+    return (fa * n + b) * n + c;
+}
+
+template <bool RGB>
+__global__ void __launch_bounds__(kThreads, 1) points_fused_kernel(const __grid_constant__ PointsK K) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    Smem S;
+    S.base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* const sb = S.base;
+    uint32_t* const sTmem = reinterpret_cast<uint32_t*>(sb + kOffBar + kNumBars * 8);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool grid = K.coords == nullptr;
+
+    const long long n_tiles_all = (K.total + 127) / 128;
+    // tiles are dealt round-robin: the skipped border tiles of a trimmed grid are spread evenly over the CTAs
+    const long long t_begin = blockIdx.x, t_end = n_tiles_all, t_step = gridDim.x;
+    // a tile of the voxel grid is skipped when every one of its points falls into the trimmed border
+    auto tile_skipped = [&](long long tile) -> bool {
+        if (!grid || K.pad <= 0) return false;
+        const long long first = K.head + tile * 128, last = min(K.head + K.total, first + 128) - 1;
+        const long long n = K.grid_n, r0 = first / n, r1 = last / n;           // rows (a, b) touched: at most r0 .. r1
+        for (long long r = r0; r <= r1; ++r) {
+            const long long a = r / n, b = r - a * n, fa = n - 1 - a;
+            if (!(fa < K.pad || fa >= n - K.pad || b < K.pad || b >= n - K.pad)) return false;
+        }
+        return true;
+    };
+
+    if (tid == 0) {
+        init_pipeline_barriers(S);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kWarps - 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    stage_decoder(sb, K.w0, K.b0, K.w1, K.b1, tid);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *sTmem;
+
+    if (warp == kWarps - 1) {                                      // ---- MMA issuer
+        if (lane == 0) {
+            int i = 0;
+            for (long long tile = t_begin; tile < t_end; tile += t_step) {
+                if (tile_skipped(tile)) continue;
+                mma_layer1(S, tmem, i);
+                if (i > 0) {
+                    mbar_wait_sleep(S.bar(BAR_HFULL + ((i - 1) & 1)), (uint32_t)(((i - 1) >> 1) & 1));
+                    tc_fence_after();
+                    mma_layer2_issue(S, tmem, (i - 1) & 1, kColSlot + 32u * ((i - 1) & 1), RGB);
+                }
+                ++i;
+            }
+            if (i > 0) {
+                mbar_wait_sleep(S.bar(BAR_HFULL + ((i - 1) & 1)), (uint32_t)(((i - 1) >> 1) & 1));
+                tc_fence_after();
+                mma_layer2_issue(S, tmem, (i - 1) & 1, kColSlot + 32u * ((i - 1) & 1), RGB);
+            }
+        }
+    } else if (warp >= kEWarps) {                                  // ---- gather warps
+        const int gw = warp - kEWarps;
+        uint2* const taps = reinterpret_cast<uint2*>(sb + kOffTaps + gw * kTapBytesPerWarp);
+        int next_item = gw, i = 0;
+        for (long long tile = t_begin; tile < t_end; tile += t_step) {
+            if (tile_skipped(tile)) continue;
+            while (next_item < i * 4 + 4) {
+                const int q = next_item - i * 4;
+                const long long g = tile * 128 + q * 32 + lane;
+                bool valid = g < K.total;
+                float px = 0.f, py = 0.f, pz = 0.f;
+                uint32_t img = 0;
+                if (valid) {
+                    if (grid) {
+                        bool border;
+                        grid_dest(K, K.head + g, border);
+                        valid = !border;
+                        grid_point(K, K.head + g, px, py, pz);
+                    } else {
+                        const float* c = K.coords + g * 3;
+                        px = __ldg(c); py = __ldg(c + 1); pz = __ldg(c + 2);
+                        img = (uint32_t)(g / K.Pn) * (uint32_t)(3 * K.PH * K.PW * 128);
+                    }
+                }
+                setup_taps(taps, lane, px, py, pz, valid, img, K.PH, K.PW, K.scale);
+                __syncwarp();
+                const int b = i % kNF;
+                if (i >= kNF) mbar_wait_sleep(S.bar(BAR_FEMPTY + b), (uint32_t)((i / kNF - 1) & 1), 40u);
+                gather_rows(K.planes, taps, sb + kOffF + b * 16384, sb + kOffF + b * 16384 + 8192, q * 32, lane);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(S.bar(BAR_FFULL + b));
+                next_item += kGWarps;
+            }
+            ++i;
+        }
+    } else {                                                       // ---- epilogue warps
+        const int eset = warp >> 2, q = warp & 3;
+        const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+        const float* const sB1c = reinterpret_cast<const float*>(sb + kOffBias) + 64;
+        long long pend_tile = -1;
+        int pend_i = 0;
+        auto epi2 = [&]() {
+            const float sg = read_sigma_tile(S, tlane, pend_i);
+            const long long g = pend_tile * 128 + q * 32 + lane;
+            if (RGB) {
+                uint32_t v[16];
+                tmem_ld16_nowait(tlane + kColSlot + 32u * (pend_i & 1) + 16u * eset, v);
+                tmem_wait_ld();
+                reg_fence16(v);
+                if (g < K.total) {
+                    const float4* bc4 = reinterpret_cast<const float4*>(sB1c + 16 * eset);
+                    float4* dst = reinterpret_cast<float4*>(K.rgb + g * kFeat + 16 * eset);
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        const float4 bb = bc4[c4];
+                        float4 o;                                   // sigmoid(x) * 1.002 - 0.001 (triplane_next3d.py:369-370)
+                        o.x = fmaf(rcp_approx(1.f + ex2_approx(__uint_as_float(v[c4 * 4]) + bb.x)), 1.002f, -0.001f);
+                        o.y = fmaf(rcp_approx(1.f + ex2_approx(__uint_as_float(v[c4 * 4 + 1]) + bb.y)), 1.002f, -0.001f);
+                        o.z = fmaf(rcp_approx(1.f + ex2_approx(__uint_as_float(v[c4 * 4 + 2]) + bb.z)), 1.002f, -0.001f);
+                        o.w = fmaf(rcp_approx(1.f + ex2_approx(__uint_as_float(v[c4 * 4 + 3]) + bb.w)), 1.002f, -0.001f);
+                        dst[c4] = o;
+                    }
+                }
+            }
+            if (eset == 0 && g < K.total) {
+                if (grid) {
+                    bool border;
+                    const long long d = grid_dest(K, K.head + g, border);
+                    K.sigma[d] = border ? K.pad_value : sg;
+                } else {
+                    K.sigma[g] = sg;
+                }
+            }
+        };
+        int i = 0;
+        for (long long tile = t_begin; tile < t_end; tile += t_step) {
+            if (tile_skipped(tile)) {                              // whole tile in the trimmed border: only the pad value is written
+                const long long g = tile * 128 + q * 32 + lane;
+                if (eset == 0 && g < K.total) { bool border; K.sigma[grid_dest(K, K.head + g, border)] = K.pad_value; }
+                continue;
+            }
+            epi1_tile(S, tlane, eset, lane, i);
+            if (pend_tile >= 0) epi2();
+            pend_tile = tile; pend_i = i;
+            ++i;
+        }
+        if (pend_tile >= 0) epi2();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kWarps - 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    }
+}
+
 struct DeviceInfo {
-    bool configured16 = false, configured32 = false;
+    bool configured16 = false, configured32 = false, configured_pts = false;
     int num_sms = 0;
 };
 DeviceInfo g_dev[64];
@@ -957,5 +1186,48 @@ int n3d_render_fused_launch(const N3DRender* p, void* stream, int mode) {
     if (L == 16) render_fused_kernel<16><<<grid, kThreads, smem, (cudaStream_t)stream>>>(K);
     else render_fused_kernel<32><<<grid, kThreads, smem, (cudaStream_t)stream>>>(K);
     N3D_CHECK_LAUNCH("n3d_render_rays");
+    return N3D_OK;
+}
+
+// coords != nullptr: arbitrary points [N, Pn, 3].  coords == nullptr: voxel grid of `grid_n`^3 points (image 0), flat indices
+// head .. head + Pn - 1, sigma written flipped + trimmed into the [grid_n]^3 output.
+int n3d_points_fused_launch(const float* planes, int N, int PH, int PW, const float* coords, long long Pn, float box_warp, const float* w0,
+                            const float* b0, const float* w1, const float* b1, float* sigma, float* rgb, int grid_n, float cube_length, long long head,
+                            int pad, float pad_value, void* stream) {
+    PointsK K;
+    K.planes = planes; K.N = N; K.PH = PH; K.PW = PW; K.coords = coords; K.Pn = Pn; K.total = (long long)N * Pn;
+    K.scale = 2.f / box_warp;
+    K.w0 = w0; K.b0 = b0; K.w1 = w1; K.b1 = b1; K.sigma = sigma; K.rgb = rgb;
+    K.grid_n = grid_n; K.pad = pad; K.pad_value = pad_value; K.head = head;
+    K.voxel_size = 0.f; K.org0 = K.org1 = K.org2 = 0.f;
+    if (!coords) {       // create_samples: voxel_origin = [0,0,0] - cube_length / 2 (float64), voxel_size = cube_length / (N - 1); both enter
+                         // the float32 tensor expression as scalars, i.e. rounded to float32
+        K.voxel_size = (float)((double)cube_length / (double)(grid_n - 1));
+        K.org0 = K.org1 = K.org2 = (float)(0.0 - (double)cube_length / 2.0);
+    }
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+        n3d_set_error("n3d_sample_points: cannot query the current device");
+        return N3D_ERR_CUDA;
+    }
+    DeviceInfo& D = g_dev[dev];
+    const size_t smem = (size_t)kSmemBytes + 1024;
+    if (!D.num_sms) {
+        cudaDeviceGetAttribute(&D.num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (D.num_sms <= 0) D.num_sms = 148;
+    }
+    if (!D.configured_pts) {
+        if (cudaFuncSetAttribute(points_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+            cudaFuncSetAttribute(points_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            n3d_set_error("n3d_sample_points: cannot raise dynamic shared memory");
+            return N3D_ERR_CUDA;
+        }
+        D.configured_pts = true;
+    }
+    const long long tiles = (K.total + 127) / 128;
+    const int grid = (int)(tiles < D.num_sms ? tiles : D.num_sms);
+    if (rgb) points_fused_kernel<true><<<grid, kThreads, smem, (cudaStream_t)stream>>>(K);
+    else points_fused_kernel<false><<<grid, kThreads, smem, (cudaStream_t)stream>>>(K);
+    N3D_CHECK_LAUNCH("n3d_sample_points");
     return N3D_OK;
 }

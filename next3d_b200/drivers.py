@@ -44,13 +44,15 @@ def to_uint8_hwc(img):
     return (img * 127.5 + 128).clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
 
 
-def render_frames(G, ws_frames, cams, verts, batch=8, image_mode='image', noise_mode='const', device=None, seed=None):
+def render_frames(G, ws_frames, cams, verts, batch=8, image_mode='image', noise_mode='const', device=None, seed=None, sampler_noise=None):
     """Yield one uint8 HWC numpy frame per (ws, camera, mesh) triple, in order, rendering `batch` frames per synthesis call.
 
     ws_frames [F, L, D], cams [F, 25], verts: [F, V, 3] / [1, V, 3] (static mesh) tensors, or an iterable of per-frame [1, V, 3]
     tensors (e.g. inputs.FramePrefetcher).  The last, partial batch is padded by repeating its final frame (one graph shape) and
     the padding is dropped.  The device->host copy of batch i overlaps the synthesis of batch i+1.  `seed`: base seed of the ray
-    sampler's RNG (batch k uses seed + k); None = a fresh random seed per call, like the reference's torch.rand."""
+    sampler's RNG (batch k uses seed + k); None = a fresh random seed per call, like the reference's torch.rand.
+    `sampler_noise=(u_coarse [F, M, Dc, 1], u_fine [F, M, Df])`: per-frame sampler uniforms instead of the in-kernel RNG (parity tests:
+    frame f gets the same noise whichever batch slot it lands in)."""
     device = device or next(G.parameters()).device
     F = ws_frames.shape[0]
     cuda = torch.device(device).type == 'cuda'
@@ -80,6 +82,9 @@ def render_frames(G, ws_frames, cams, verts, batch=8, image_mode='image', noise_
         else:
             v = verts[idx].to(device, torch.float32, non_blocking=True)
         kw = {} if seed is None else {'seed': int(seed) + b0 // batch}
+        if sampler_noise is not None:
+            u_c, u_f = sampler_noise
+            kw['sampler_noise'] = (u_c[idx], u_f[idx].reshape(-1, u_f.shape[-1]))
         img = G.synthesis(w, c, v, noise_mode=noise_mode, **kw)[image_mode]
         if image_mode == 'image_depth':                          # gen_videos_next3d.py:160-162, per frame
             img = -img
@@ -140,17 +145,14 @@ def trim_sigma_grid(sigmas, shape_res, pad_value=-1000.0):
 def extract_sigma_grid(G, ws, v, shape_res=512, max_batch=1000000, noise_mode='const'):
     """Density grid for marching cubes (gen_samples_next3d.py:208-238) -> float32 numpy [R,R,R], flipped and trimmed like the
     script's.  The tri-planes are computed ONCE (the script's G.sample re-runs the three backbones for every 1M-point chunk: 17
-    times at 256^3, 135 times at 512^3), the query points are generated on the device chunk by chunk and only sigma is decoded."""
+    times at 256^3, 135 times at 512^3), the query points are generated inside the decoding kernel and only sigma is decoded."""
     from . import kernels as K
     eng = G._get_engine()
     eng.rk = G.rendering_kwargs
     planes = eng.compute_planes(ws, v, noise_mode)
-    dev = planes.device
-    total = shape_res ** 3
-    sigmas = torch.empty(total, device=dev)
     box = G.rendering_kwargs['box_warp']
-    for head in range(0, total, max_batch):
-        n = min(max_batch, total - head)
-        coords = create_samples(shape_res, box * 1, head, n, device=dev)
-        K.sample_points(planes[:1], coords.contiguous(), box, eng.dec, sigmas[head:head + n].view(1, n), None)
-    return trim_sigma_grid(sigmas.view(shape_res, shape_res, shape_res), shape_res).cpu().numpy()
+    sigmas = torch.empty(shape_res, shape_res, shape_res, device=planes.device)
+    # one launch: voxel centres generated in the kernel (bit-identical to create_samples), flip + border trim fused into the store,
+    # border voxels (55 % of a 256^3 grid) never decoded.  max_batch is kept for API compatibility with the script's chunk size.
+    K.sample_grid(planes[0], shape_res, box * 1, box, eng.dec, sigmas, pad=int(30 * shape_res / 256))
+    return sigmas.cpu().numpy()

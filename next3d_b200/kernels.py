@@ -215,3 +215,11 @@ def sample_points(planes, coords, box_warp, dec, sigma, rgb=None):
     Pn = coords.shape[1]
     check(lib.n3d_sample_points(ptr(planes), N, PH, PW, ptr(coords), Pn, float(box_warp), *(ptr(t) for t in dec), ptr(sigma), ptr(rgb),
                                 stream_ptr()), 'n3d_sample_points')
+
+
+def sample_grid(planes, grid_n, cube_length, box_warp, dec, sigma_grid, head=0, count=None, pad=0, pad_value=-1000.0):
+    """sigma of the create_samples voxel grid (in-kernel coordinates), written flipped + trimmed into sigma_grid [grid_n]^3."""
+    _, PH, PW, _ = planes.shape[-4:]
+    count = grid_n ** 3 - head if count is None else count
+    check(lib.n3d_sample_grid(ptr(planes), PH, PW, grid_n, float(cube_length), float(box_warp), head, count, pad, float(pad_value),
+                              *(ptr(t) for t in dec), ptr(sigma_grid), stream_ptr()), 'n3d_sample_grid')

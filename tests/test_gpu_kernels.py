@@ -452,5 +452,5 @@ def test_sample_points(K):
     sigma = torch.zeros(1, 5000, device=DEV)
     rgb = torch.zeros(1, 5000, 32, device=DEV)
     K.sample_points(planes.permute(0, 1, 3, 4, 2).contiguous().to(DEV), coords.to(DEV), 1.0, dec, sigma, rgb)
-    assert range_rel_err(sigma.cpu(), sig_ref[..., 0]) < 1e-5
-    assert range_rel_err(rgb.cpu(), rgb_ref) < 1e-5
+    assert range_rel_err(sigma.cpu(), sig_ref[..., 0]) < 3e-5         # decoder on tcgen05, bf16x3 (~2^-16 per product)
+    assert range_rel_err(rgb.cpu(), rgb_ref) < 3e-5

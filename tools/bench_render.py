@@ -29,3 +29,15 @@ for i in range(10):
     ts.append(e0.elapsed_time(e1))
 ts.sort()
 print(which, 'N3D_RENDER_MODE', os.environ.get('N3D_RENDER_MODE', '0'), 'render_fused_kernel median', ts[len(ts) // 2], 'ms  min', ts[0], 'ms', flush=True)
+if which == 'c2' and os.environ.get('N3D_BENCH_GRID', '1') == '1':
+    Rg = 256
+    out = torch.empty(Rg, Rg, Rg, device='cuda')
+    for pad in (0, int(30 * Rg / 256)):
+        for _ in range(2):
+            K.sample_grid(planes[0], Rg, 1.0, 1.0, dec, out, pad=pad)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            K.sample_grid(planes[0], Rg, 1.0, 1.0, dec, out, pad=pad)
+        e1.record(); torch.cuda.synchronize()
+        print(f'c5 grid {Rg}^3 pad {pad}: {e0.elapsed_time(e1) / 5:.3f} ms per grid', flush=True)
