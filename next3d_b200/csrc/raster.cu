@@ -14,7 +14,9 @@ inline int grid_for(int64_t work_items, int threads, int per_sm = 8) {
 }
 
 // ---------------------------------------------------------------------------------------------- transform
-// p' = ((p*[1,-1,1]) @ R + [0,-.01,-.01]) * 5 ; y,z negated ; z += zoff ; optional NDC x,y negation.
+// p' = ((p*[1,-1,1]) @ R + [0,-.01,-.01]) * 5 ; y,z negated ; z += zoff ; optional NDC x,y negation.  The 3-term dot products
+// are evaluated as the fused chain fma(z, R2j, fma(y, R1j, x * R0j)) -- what torch.bmm's CPU kernel computes for K = 3 -- so the
+// view-space vertices, and with them the rasterizer's index buffer, are bit-identical to the oracle's.
 __global__ void __launch_bounds__(256) transform_kernel(const float* __restrict__ pts, int N, int P, const float* __restrict__ rot,
                                                         int nviews, float zoff, int ndc_flip, float* __restrict__ out) {
     const int64_t total = (int64_t)N * nviews * P;
@@ -28,7 +30,7 @@ __global__ void __launch_bounds__(256) transform_kernel(const float* __restrict_
         float r[3];
 #pragma unroll
         for (int j = 0; j < 3; ++j)
-            r[j] = __fadd_rn(__fadd_rn(__fmul_rn(x, R[j]), __fmul_rn(y, R[3 + j])), __fmul_rn(z, R[6 + j]));
+            r[j] = __fmaf_rn(z, R[6 + j], __fmaf_rn(y, R[3 + j], __fmul_rn(x, R[j])));       // k = 0, 1, 2 FMA chain (see oracle.transform_view)
         float ox = __fmul_rn(__fadd_rn(r[0], 0.f), 5.f);
         float oy = -__fmul_rn(__fadd_rn(r[1], -0.01f), 5.f);
         float oz = __fadd_rn(-__fmul_rn(__fadd_rn(r[2], -0.01f), 5.f), zoff);

@@ -152,12 +152,24 @@ def angle2matrix(angles_deg):
                         -sy, cy * sx, cy * cx]).reshape(3, 3)
 
 
+def _bmm3_fma(p, R):
+    """torch.bmm(p [N,P,3], R [N,3,3]) with the summation order written out: the reference's bmm (renderer.py:505-514 via
+    triplane_next3d.py:197) leaves it to the BLAS; oneMKL's fp32 kernel evaluates K = 3 as the fused chain
+    fma(p2, R2j, fma(p1, R1j, p0 * R0j)) (checked bit for bit in tests/test_oracle_vs_reference.py).  Each fma is emulated in
+    float64, where the product of two float32 is exact, so the result does not depend on the BLAS of the machine running the
+    oracle and the CUDA kernel can reproduce it exactly."""
+    p64, R64 = p.double(), R.double()
+    acc = (p64[:, :, 0:1] * R64[:, 0:1, :]).float()
+    acc = (p64[:, :, 1:2] * R64[:, 1:2, :] + acc.double()).float()
+    return (p64[:, :, 2:3] * R64[:, 2:3, :] + acc.double()).float()
+
+
 def transform_view(points, view):
     """(v*[1,-1,1]) @ R + shift, *5, orth-proj with camera [1,0,0] (identity), negate y,z (triplane_next3d.py:194-205)."""
     p = points.clone()
     p[..., 1] *= -1
     R = angle2matrix(view)[None].expand(p.shape[0], -1, -1)
-    p = (torch.bmm(p, R) + torch.tensor([[0, -0.01, -0.01]])) * torch.tensor([[5.0]])
+    p = (_bmm3_fma(p, R) + torch.tensor([[0, -0.01, -0.01]])) * torch.tensor([[5.0]])
     cam = torch.tensor([1., 0., 0.]).view(-1, 1, 3)
     p = torch.cat([p[:, :, :2] + cam[:, :, 1:], p[:, :, 2:]], 2) * cam[:, :, 0:1]
     p[:, :, 1:] = -p[:, :, 1:]

@@ -108,3 +108,15 @@ def test_full_synthesis_bit_exact(ref):
         o = og.synthesis(sd, cfg, ws, c_cam, v, u_c, u_f)
     for k in ('image', 'image_raw', 'image_depth'):
         assert (o[k] - r[k]).abs().max().item() <= 1e-6 * r[k].abs().max().item(), k
+
+
+def test_view_transform_is_the_blas_fma_chain(ref):
+    """oracle.generator._bmm3_fma (explicit k = 0,1,2 fused chain, float64-emulated) == torch.bmm bit for bit: pins the summation
+    order the reference's bmm (renderer.py:505-514) takes on this machine, which the CUDA transform kernel reproduces."""
+    g = torch.Generator().manual_seed(0)
+    p = torch.randn(3, 5023, 3, generator=g)
+    R = torch.randn(3, 3, 3, generator=g)
+    assert torch.equal(og._bmm3_fma(p, R), torch.bmm(p, R))
+    for view in ((0, 0, 0), (0, 90, 0), (0, -90, 0), (90, 0, 0)):
+        Rv = og.angle2matrix(torch.tensor(view, dtype=torch.float32))[None].expand(3, -1, -1)
+        assert torch.equal(og._bmm3_fma(p, Rv), torch.bmm(p, Rv))
