@@ -35,10 +35,15 @@ class GeneratorConfig:
     c_dim: int = 25
     plane_res: int = 256               # resolution of texture / static / blended planes
     plane_ch: int = 32
+    sr_num_fp16_res: int = 4           # train_next3d.py:196 default; > 0 => SR blocks clamp at +-256 (superresolution.py:271-277)
 
     @property
     def sr_module(self):
         return {512: '8XDC', 256: '4X'}[self.img_resolution]
+
+    @property
+    def sr_clamp(self):
+        return 256.0 if self.sr_num_fp16_res > 0 else None
 
     def channels(self, res):
         return min(self.channel_base // res, self.channel_max)

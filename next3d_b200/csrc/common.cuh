@@ -33,6 +33,15 @@ void n3d_set_error(const char* fmt, ...);
 
 static inline int n3d_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Host-side facts cached PER DEVICE (the library holds no device memory and no device-global state): SM count and which kernels
+// already had their dynamic shared-memory limit raised on that device.  Indexed by the current device at call time.
+struct N3DDeviceState {
+    int num_sms;
+    unsigned configured;     // bit per kernel, see N3D_CFG_*
+};
+enum { N3D_CFG_CONV = 1u, N3D_CFG_FILL_MOUTH = 2u, N3D_CFG_RENDER16 = 4u, N3D_CFG_RENDER32 = 8u, N3D_CFG_POINTS = 16u };
+N3DDeviceState* n3d_device_state(void);      // api.cu; nullptr (+ error message) when the current device cannot be queried
+
 // fp32 -> (hi, lo) bf16 pair with hi + lo ~= x to ~16 mantissa bits (used by the 3-product tensor-core scheme).
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
     hi = __float2bfloat16_rn(x);

@@ -425,7 +425,6 @@ int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
 
 int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
-int* g_err_flag = nullptr;   // device int, lazily allocated once per process; only written when a kernel traps
 
 }  // namespace
 
@@ -524,11 +523,7 @@ int launch_conv(const N3DConvGemm* p, int nsub, const SubSpec* specs, void* stre
     K.f32_accumulate = p->f32_accumulate;
     K.rgb = p->rgb;
     K.oy_mul = p->oy_mul; K.ox_mul = p->ox_mul; K.OH = p->OH; K.OW = p->OW;
-    if (!g_err_flag) {
-        if (cudaMalloc(&g_err_flag, sizeof(int)) != cudaSuccess) { n3d_set_error("n3d_conv_gemm: cudaMalloc(err flag) failed"); return N3D_ERR_CUDA; }
-        cudaMemset(g_err_flag, 0, sizeof(int));
-    }
-    K.err_flag = g_err_flag;
+    K.err_flag = nullptr;       // a protocol timeout traps (the launch fails with an error); no device-side flag is kept
 
     const uint64_t adims[4] = {(uint64_t)p->Cin, (uint64_t)p->AW, (uint64_t)p->AH, (uint64_t)p->NI};
     const uint32_t abox[4] = {(uint32_t)K.block_k, (uint32_t)K.TW, (uint32_t)K.tile_h, (uint32_t)K.TN};
@@ -543,22 +538,17 @@ int launch_conv(const N3DConvGemm* p, int nsub, const SubSpec* specs, void* stre
     }
 
     const int smem = K.stages * K.stage_bytes + 8 * (2 * K.stages + 4) + 32 + 2 * kStageArrays * kMaxBlockN * 4 + 1024;
-    static int smem_configured = 0;
-    if (smem > smem_configured) {
+    N3DDeviceState* D = n3d_device_state();
+    if (!D) return N3D_ERR_CUDA;
+    if (!(D->configured & N3D_CFG_CONV)) {
         if (cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
             n3d_set_error("n3d_conv_gemm: cannot raise dynamic shared memory to 227 KiB");
             return N3D_ERR_CUDA;
         }
-        smem_configured = 227 * 1024;
+        D->configured |= N3D_CFG_CONV;
     }
     const int total_tiles = tiles_m * K.tiles_n;
-    static int num_sms = 0;
-    if (!num_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (num_sms <= 0) num_sms = 148;
-    }
+    const int num_sms = D->num_sms;
     const int grid = min(total_tiles, num_sms);
     conv_gemm_kernel<<<grid, kThreads, smem, st>>>(K);
     N3D_CHECK_LAUNCH("n3d_conv_gemm");

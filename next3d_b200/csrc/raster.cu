@@ -535,13 +535,14 @@ extern "C" int n3d_uv_sample(const int32_t* pix_to_face, const float* bary, cons
 extern "C" int n3d_fill_mouth(float* alpha, int NI, int H, int W, void* stream) {
     N3D_CHECK_ARG(alpha && NI > 0 && H > 0 && W > 0, "n3d_fill_mouth: bad args");
     N3D_CHECK_ARG((int64_t)H * (W + 4) <= 200 * 1024, "n3d_fill_mouth: image %dx%d too large for the shared-memory state map", H, W);
-    static bool configured = false;
-    if (!configured) {
+    N3DDeviceState* D = n3d_device_state();
+    if (!D) return N3D_ERR_CUDA;
+    if (!(D->configured & N3D_CFG_FILL_MOUTH)) {
         if (cudaFuncSetAttribute(fill_mouth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
             n3d_set_error("n3d_fill_mouth: cannot raise dynamic shared memory");
             return N3D_ERR_CUDA;
         }
-        configured = true;
+        D->configured |= N3D_CFG_FILL_MOUTH;
     }
     fill_mouth_kernel<<<NI, 1024, (size_t)H * (W + 4), (cudaStream_t)stream>>>(alpha, H, W);
     N3D_CHECK_LAUNCH("n3d_fill_mouth");

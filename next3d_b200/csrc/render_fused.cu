@@ -1135,12 +1135,6 @@ __global__ void __launch_bounds__(kThreads, 1) points_fused_kernel(const __grid_
     }
 }
 
-struct DeviceInfo {
-    bool configured16 = false, configured32 = false, configured_pts = false;
-    int num_sms = 0;
-};
-DeviceInfo g_dev[64];
-
 }  // namespace
 
 int n3d_render_fused_launch(const N3DRender* p, void* stream, int mode) {
@@ -1161,28 +1155,20 @@ int n3d_render_fused_launch(const N3DRender* p, void* stream, int mode) {
     K.gpi = K.blocks_x * blocks_y * 32;
     K.total_groups = (long long)p->N * K.gpi;
     K.mode = mode;
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
-        n3d_set_error("n3d_render_rays: cannot query the current device");
-        return N3D_ERR_CUDA;
-    }
-    DeviceInfo& D = g_dev[dev];
+    N3DDeviceState* D = n3d_device_state();
+    if (!D) return N3D_ERR_CUDA;
     const size_t smem = (size_t)kSmemBytes + 1024;
-    if (!D.num_sms) {
-        cudaDeviceGetAttribute(&D.num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (D.num_sms <= 0) D.num_sms = 148;
-    }
-    bool& configured = L == 16 ? D.configured16 : D.configured32;
-    if (!configured) {
+    const unsigned bit = L == 16 ? N3D_CFG_RENDER16 : N3D_CFG_RENDER32;
+    if (!(D->configured & bit)) {
         const cudaError_t e = L == 16 ? cudaFuncSetAttribute(render_fused_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                                       : cudaFuncSetAttribute(render_fused_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             n3d_set_error("n3d_render_rays: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
             return N3D_ERR_CUDA;
         }
-        configured = true;
+        D->configured |= bit;
     }
-    const int grid = (int)(K.total_groups < D.num_sms ? K.total_groups : D.num_sms);
+    const int grid = (int)(K.total_groups < D->num_sms ? K.total_groups : D->num_sms);
     if (L == 16) render_fused_kernel<16><<<grid, kThreads, smem, (cudaStream_t)stream>>>(K);
     else render_fused_kernel<32><<<grid, kThreads, smem, (cudaStream_t)stream>>>(K);
     N3D_CHECK_LAUNCH("n3d_render_rays");
@@ -1205,27 +1191,19 @@ int n3d_points_fused_launch(const float* planes, int N, int PH, int PW, const fl
         K.voxel_size = (float)((double)cube_length / (double)(grid_n - 1));
         K.org0 = K.org1 = K.org2 = (float)(0.0 - (double)cube_length / 2.0);
     }
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
-        n3d_set_error("n3d_sample_points: cannot query the current device");
-        return N3D_ERR_CUDA;
-    }
-    DeviceInfo& D = g_dev[dev];
+    N3DDeviceState* D = n3d_device_state();
+    if (!D) return N3D_ERR_CUDA;
     const size_t smem = (size_t)kSmemBytes + 1024;
-    if (!D.num_sms) {
-        cudaDeviceGetAttribute(&D.num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (D.num_sms <= 0) D.num_sms = 148;
-    }
-    if (!D.configured_pts) {
+    if (!(D->configured & N3D_CFG_POINTS)) {
         if (cudaFuncSetAttribute(points_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
             cudaFuncSetAttribute(points_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
             n3d_set_error("n3d_sample_points: cannot raise dynamic shared memory");
             return N3D_ERR_CUDA;
         }
-        D.configured_pts = true;
+        D->configured |= N3D_CFG_POINTS;
     }
     const long long tiles = (K.total + 127) / 128;
-    const int grid = (int)(tiles < D.num_sms ? tiles : D.num_sms);
+    const int grid = (int)(tiles < D->num_sms ? tiles : D->num_sms);
     if (rgb) points_fused_kernel<true><<<grid, kThreads, smem, (cudaStream_t)stream>>>(K);
     else points_fused_kernel<false><<<grid, kThreads, smem, (cudaStream_t)stream>>>(K);
     N3D_CHECK_LAUNCH("n3d_sample_points");

@@ -34,16 +34,24 @@ def shard_range(total, rank, world):
     return start, start + base + (1 if rank < extra else 0)
 
 
-def gather_images(local_images, dst=0):
-    """Gather equally-sized per-rank image batches to `dst`: returns [world*B, ...] on dst, None elsewhere."""
+def gather_images(local_images, dst=0, sizes=None):
+    """Gather per-rank image batches to `dst`: returns [sum(B_r), ...] on dst (rank order), None elsewhere.  `sizes`: batch size of
+    every rank when the shards are unequal (shard_range with total % world != 0) -- smaller shards are padded to the largest for
+    the collective and trimmed on dst; None = all ranks hold the same number of images."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return local_images
     world, rank = dist.get_world_size(), dist.get_rank()
+    bmax = local_images.shape[0] if sizes is None else max(sizes)
+    send = local_images.contiguous()
+    if send.shape[0] < bmax:
+        send = torch.cat([send, send.new_zeros((bmax - send.shape[0],) + tuple(send.shape[1:]))], 0)
     if rank == dst:
-        out = torch.empty((world,) + tuple(local_images.shape), dtype=local_images.dtype, device=local_images.device)
-        dist.gather(local_images.contiguous(), list(out.unbind(0)), dst=dst)
-        return out.flatten(0, 1)
-    dist.gather(local_images.contiguous(), None, dst=dst)
+        out = torch.empty((world,) + tuple(send.shape), dtype=send.dtype, device=send.device)
+        dist.gather(send, list(out.unbind(0)), dst=dst)
+        if sizes is None:
+            return out.flatten(0, 1)
+        return torch.cat([out[r, :sizes[r]] for r in range(world)], 0)
+    dist.gather(send, None, dst=dst)
     return None
 
 

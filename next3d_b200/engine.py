@@ -155,9 +155,9 @@ class Engine:
             p = f'superresolution.block{blk}'
             noise = self.rk['superresolution_noise_mode'] != 'none'
             # ws = eg3d_ws[:, -1:].repeat(1, 3, 1) (superresolution.py:280): every SR layer reads ws index 13
-            self._add_mod(sd, f'{p}.conv0', cin, cout, 3, up, 13, clamp=256.0, noise=noise)
-            self._add_mod(sd, f'{p}.conv1', cout, cout, 3, 1, 13, clamp=256.0, noise=noise)
-            self._add_mod(sd, f'{p}.torgb', cout, 3, 1, 1, 13, is_rgb=True, clamp=256.0)
+            self._add_mod(sd, f'{p}.conv0', cin, cout, 3, up, 13, clamp=cfg.sr_clamp, noise=noise)
+            self._add_mod(sd, f'{p}.conv1', cout, cout, 3, 1, 13, clamp=cfg.sr_clamp, noise=noise)
+            self._add_mod(sd, f'{p}.torgb', cout, 3, 1, 1, 13, is_rgb=True, clamp=cfg.sr_clamp)
         # decoder (OSGDecoder, triplane_next3d.py:348-357): FullyConnectedLayer gains folded like its forward does
         self.dec = ((sd['decoder.net.0.weight'].float() * (1.0 / math.sqrt(32))).contiguous(), sd['decoder.net.0.bias'].float().contiguous(),
                     (sd['decoder.net.2.weight'].float() * (1.0 / math.sqrt(64))).contiguous(), sd['decoder.net.2.bias'].float().contiguous())
@@ -446,6 +446,9 @@ class Engine:
         c0, c1 = _config.sr_channels(cfg)
         need = (R != 128) if cfg.sr_module == '8XDC' else (R < 128)
         r0 = 128 if need else R
+        if need and R > 128 and not self.rk.get('sr_antialias', True):
+            raise RuntimeError('next3d_b200: sr_antialias=False with a neural rendering resolution above 128 (a plain bilinear minification) is not '
+                               'implemented')
         x = Split((N, r0, r0, cfg.plane_ch), dev)
         rgb_lo = feat[..., :3].contiguous()                                    # image_raw channels (tiny copy)
         if need:
@@ -479,8 +482,21 @@ class Engine:
         self.launches += 1
 
     # ------------------------------------------------------------------------------------------ planes + synthesis
+    def _on_device(self, **tensors):
+        """Inputs must live on the engine's device: raw device pointers are handed to the C ABI, so a CPU or other-GPU tensor
+        would become an illegal address instead of a clean error."""
+        for name, t in tensors.items():
+            if t is not None and t.device != self.device:
+                raise RuntimeError(f'next3d_b200: `{name}` is on {t.device} but the generator runs on {self.device}; move it there '
+                                   f'(there is no CPU path)')
+
     def compute_planes(self, ws, v, noise_mode='const', return_intermediates=False):
         """Everything up to the blended tri-planes (triplane_next3d.py:137-174) -> [N,3,256,256,32] channels-last fp32."""
+        self._on_device(ws=ws, v=v)
+        with torch.cuda.device(self.device):
+            return self._compute_planes(ws, v, noise_mode, return_intermediates)
+
+    def _compute_planes(self, ws, v, noise_mode='const', return_intermediates=False):
         cfg, dev = self.cfg, self.device
         N = ws.shape[0]
         self._N = N
@@ -552,12 +568,18 @@ class Engine:
 
     def synthesis(self, ws, c, v, noise_mode='const', neural_rendering_resolution=None, sampler_noise=None, seed=0,
                   return_intermediates=False, seed_ptr=None):
+        self._on_device(ws=ws, c=c, v=v)
+        with torch.cuda.device(self.device):
+            return self._synthesis(ws, c, v, noise_mode, neural_rendering_resolution, sampler_noise, seed, return_intermediates, seed_ptr)
+
+    def _synthesis(self, ws, c, v, noise_mode='const', neural_rendering_resolution=None, sampler_noise=None, seed=0,
+                   return_intermediates=False, seed_ptr=None):
         cfg, dev = self.cfg, self.device
         N = ws.shape[0]
         R = neural_rendering_resolution or cfg.neural_rendering_resolution
         self.launches = 0
         self.conv_flops = 0.0
-        out = self.compute_planes(ws, v, noise_mode, return_intermediates)
+        out = self._compute_planes(ws, v, noise_mode, return_intermediates)
         planes, inter = out if return_intermediates else (out, None)
         c = c.to(torch.float32)
         cam = c[:, :16].contiguous()
@@ -585,25 +607,33 @@ class Engine:
 
     # ------------------------------------------------------------------------------------------ CUDA graph replay
     def synthesis_graphed(self, ws, c, v, noise_mode='const', neural_rendering_resolution=None, seed=0):
+        with torch.cuda.device(self.device):
+            return self._synthesis_graphed(ws, c, v, noise_mode, neural_rendering_resolution, seed)
+
+    def _synthesis_graphed(self, ws, c, v, noise_mode='const', neural_rendering_resolution=None, seed=0):
         """Same as synthesis() (in-kernel sampler RNG) but the 185 launches of one forward are captured once per
         (batch, resolution, noise_mode) into a CUDA graph and replayed: removes the host-side launch latency that otherwise
         leaves the GPU idle between kernels.  Inputs are copied into static buffers; the returned tensors are the graph's
         static outputs and are overwritten by the next call with the same key."""
+        self._on_device(ws=ws, c=c, v=v)
         R = neural_rendering_resolution or self.cfg.neural_rendering_resolution
-        key = (ws.shape[0], R, noise_mode, tuple(v.shape))
+        rk = self.rk
+        key = (ws.shape[0], R, noise_mode, tuple(v.shape), rk['depth_resolution'], rk['depth_resolution_importance'], float(rk['ray_start']),
+               float(rk['ray_end']), float(rk['box_warp']), bool(rk.get('white_back', False)), rk['superresolution_noise_mode'],
+               bool(rk.get('sr_antialias', True)))
         g = self._graphs.get(key)
         if g is None:
-            st = dict(ws=torch.empty_like(ws, dtype=torch.float32), c=torch.empty_like(c, dtype=torch.float32),
-                      v=torch.empty_like(v, dtype=torch.float32), seed=torch.zeros(1, dtype=torch.int64, device=self.device))
+            st = dict(ws=torch.empty(ws.shape, dtype=torch.float32, device=self.device), c=torch.empty(c.shape, dtype=torch.float32, device=self.device),
+                      v=torch.empty(v.shape, dtype=torch.float32, device=self.device), seed=torch.zeros(1, dtype=torch.int64, device=self.device))
             st['ws'].copy_(ws); st['c'].copy_(c); st['v'].copy_(v)
             side = torch.cuda.Stream(self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(side):                                   # warm-up outside capture (lazy attribute setup, allocator)
-                self.synthesis(st['ws'], st['c'], st['v'], noise_mode, R, seed=0, seed_ptr=st['seed'])
+                self._synthesis(st['ws'], st['c'], st['v'], noise_mode, R, seed=0, seed_ptr=st['seed'])
             torch.cuda.current_stream(self.device).wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                out = self.synthesis(st['ws'], st['c'], st['v'], noise_mode, R, seed=0, seed_ptr=st['seed'])
+                out = self._synthesis(st['ws'], st['c'], st['v'], noise_mode, R, seed=0, seed_ptr=st['seed'])
             g = self._graphs[key] = (graph, st, out, self.launches, self.conv_flops)
         graph, st, out, launches, flops = g
         st['ws'].copy_(ws, non_blocking=True); st['c'].copy_(c, non_blocking=True); st['v'].copy_(v, non_blocking=True)

@@ -193,6 +193,13 @@ def blend_planes(front, tex_planes, alpha, static, planes):
 def render_rays(planes, cam2world, intrinsics, res, opts, dec, rgb, depth, wsum, depth_minmax, u_coarse=None, u_fine=None, seed=0,
                 seed_ptr=None):
     """planes [N,3,PH,PW,32] channels-last; dec = (w0 [64,32], b0 [64], w1 [33,64], b1 [33]) with gains folded in."""
+    unsupported = [k for k, bad in (('disparity_space_sampling', bool(opts.get('disparity_space_sampling', False))),
+                                    ('density_noise', float(opts.get('density_noise', 0) or 0) > 0),
+                                    ('clamp_mode', opts.get('clamp_mode', 'softplus') != 'softplus'),
+                                    ('ray_start/ray_end', isinstance(opts.get('ray_start'), str) or isinstance(opts.get('ray_end'), str))) if bad]
+    if unsupported:     # renderer.py:98-107 (auto near/far), :153 (density noise), :186-196 (disparity sampling), ray_marcher.py:41-44
+        raise RuntimeError(f'libnext3d_b200 n3d_render_rays failed (code -2, unsupported): rendering option(s) {unsupported} are not '
+                           f'implemented by the fused renderer (supported: linear stratified sampling, fixed ray_start / ray_end, softplus)')
     p = _lib.Render()
     N, _, PH, PW, _ = planes.shape
     p.planes, p.N, p.PH, p.PW = ptr(planes), N, PH, PW

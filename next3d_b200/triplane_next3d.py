@@ -57,7 +57,8 @@ class TriPlaneGenerator(torch.nn.Module):
         self.neural_rendering_resolution = 64
         self.load_lms = True
         self.fill_mouth = True
-        self.uv_face_mask = torch.ones(1, 1, 256, 256)     # data/ffhq/uv_face_eye_mask.png is not shipped: synthetic all-ones
+        self.sr_num_fp16_res = sr_num_fp16_res
+        self.uv_face_mask = self._load_uv_face_mask()
         topo = None
         for name, shape, kind, _ in _config.param_spec(self.cfg):
             if kind == 'topology':
@@ -72,6 +73,27 @@ class TriPlaneGenerator(torch.nn.Module):
         self._engine = None
         self._engine_key = None
         self.use_cuda_graph = False      # opt-in: replay one captured CUDA graph per (batch, resolution) instead of 185 launches
+
+    @staticmethod
+    def _load_uv_face_mask(path='data/ffhq/uv_face_eye_mask.png'):
+        """Eye / face mask of the UV atlas (triplane_next3d.py:91-92: channel 0 of the PNG / 255, F.interpolate (nearest) to
+        256^2).  Not part of the state dict and not shipped with the reference repo: when the file is
+        absent an all-ones mask is used and a warning says so -- with a real checkpoint the alpha around the eyes then differs
+        from the reference's.  Assigning `G.uv_face_mask = ...` later is honoured (it is part of the engine cache key)."""
+        import os
+        import warnings
+        if os.path.isfile(path):
+            try:
+                import numpy as np
+                from PIL import Image
+                m = np.asarray(Image.open(path).convert('RGB'), dtype=np.float32)[:, :, 2] / 255.0   # cv2.imread is BGR: its channel 0 = blue
+                return torch.nn.functional.interpolate(torch.from_numpy(m)[None, None].contiguous(), [256, 256])
+            except Exception as e:                                                 # unreadable file: say so, keep going
+                warnings.warn(f'next3d_b200: cannot read {path} ({e}); using an all-ones UV face mask')
+        else:
+            warnings.warn(f'next3d_b200: {path} not found; using an all-ones UV face mask (set G.uv_face_mask to the real one for '
+                          f'checkpoint-faithful eyes)')
+        return torch.ones(1, 1, 256, 256)
 
     @staticmethod
     def _load_mesh(topology_path):
@@ -96,7 +118,7 @@ class TriPlaneGenerator(torch.nn.Module):
     @classmethod
     def from_config(cls, cfg, state_dict=None, device='cuda'):
         G = cls(img_resolution=cfg.img_resolution, rendering_kwargs=cfg.rendering_kwargs, channel_base=cfg.channel_base,
-                channel_max=cfg.channel_max)
+                channel_max=cfg.channel_max, sr_num_fp16_res=cfg.sr_num_fp16_res)
         G.neural_rendering_resolution = cfg.neural_rendering_resolution
         if state_dict is not None:
             G.load_state_dict(state_dict)
@@ -106,15 +128,25 @@ class TriPlaneGenerator(torch.nn.Module):
         """Re-pack weights into the engine's layouts (call after changing parameters in place)."""
         self._engine = None
 
+    def _state_version(self):
+        """Changes whenever a parameter / buffer is written in place (load_state_dict, misc.copy_params_and_buffers, .copy_())."""
+        return sum(t._version for t in self.state_dict(keep_vars=True).values())
+
     def _get_engine(self):
         dev = self.faces.device
         if dev.type != 'cuda':
             raise RuntimeError('next3d_b200.TriPlaneGenerator runs on CUDA (sm_100a) only: move the module with .to("cuda"); there is no '
                                'CPU fallback path')
-        key = (str(dev), self.img_resolution)
+        rk = self.rendering_kwargs
+        # everything the packed engine bakes in: weights (version counter), the UV mask, pack-time rendering options
+        key = (str(dev), self.img_resolution, self._state_version(), id(self.uv_face_mask), self.uv_face_mask._version,
+               rk.get('superresolution_noise_mode', 'none'), self.sr_num_fp16_res)
         if self._engine is None or self._engine_key != key:
-            self._engine = Engine(self.cfg, self.state_dict(), device=dev, uv_face_mask=self.uv_face_mask)
+            import dataclasses
+            cfg = dataclasses.replace(self.cfg, rendering_kwargs=rk, sr_num_fp16_res=self.sr_num_fp16_res)
+            self._engine = Engine(cfg, self.state_dict(), device=dev, uv_face_mask=self.uv_face_mask)
             self._engine_key = key
+        self._engine.rk = rk
         return self._engine
 
     # ------------------------------------------------------------------------------------------ reference API
@@ -155,7 +187,6 @@ class TriPlaneGenerator(torch.nn.Module):
         if seed is None:
             seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) if sampler_noise is None else 0
         eng = self._get_engine()
-        eng.rk = self.rendering_kwargs
         if self.use_cuda_graph and sampler_noise is None and not synthesis_kwargs.get('return_intermediates', False):
             return eng.synthesis_graphed(ws, c, v, noise_mode=noise_mode, neural_rendering_resolution=neural_rendering_resolution, seed=seed)
         return eng.synthesis(ws, c, v, noise_mode=noise_mode, neural_rendering_resolution=neural_rendering_resolution,
@@ -165,11 +196,13 @@ class TriPlaneGenerator(torch.nn.Module):
         """run_model on arbitrary points (triplane_next3d.py:278-323): -> {'rgb': [N,P,32], 'sigma': [N,P,1]}."""
         from . import kernels as K
         eng = self._get_engine()
+        eng._on_device(coordinates=coordinates)
         planes = eng.compute_planes(ws, v, synthesis_kwargs.get('noise_mode', 'random'))
         N, P, _ = coordinates.shape
         sigma = torch.empty(N, P, device=planes.device)
         rgb = torch.empty(N, P, 32, device=planes.device)
-        K.sample_points(planes, coordinates.to(torch.float32).contiguous(), self.rendering_kwargs['box_warp'], eng.dec, sigma, rgb)
+        with torch.cuda.device(planes.device):
+            K.sample_points(planes, coordinates.to(torch.float32).contiguous(), self.rendering_kwargs['box_warp'], eng.dec, sigma, rgb)
         return {'rgb': rgb, 'sigma': sigma[..., None]}
 
     def sample(self, coordinates, directions, z, c, v, truncation_psi=1, truncation_cutoff=None, update_emas=False, **synthesis_kwargs):

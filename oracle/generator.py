@@ -254,10 +254,11 @@ def superresolution(sd, cfg, rgb, x, ws):
         x = F.interpolate(x, size=(128, 128), mode='bilinear', align_corners=False, antialias=aa)
         rgb = F.interpolate(rgb, size=(128, 128), mode='bilinear', align_corners=False, antialias=aa)
     nm = cfg.rendering_kwargs['superresolution_noise_mode']
-    # sr_num_fp16_res=4 -> use_fp16 -> conv_clamp=256 even when executed in fp32 (superresolution.py:271-276)
-    x, rgb = synthesis_block(sd, 'superresolution.block0', x, rgb, ws, noise_mode=nm, clamp=256,
+    # sr_num_fp16_res > 0 -> use_fp16 -> conv_clamp=256 even when executed in fp32; 0 -> no clamp (superresolution.py:271-276)
+    clamp = cfg.sr_clamp
+    x, rgb = synthesis_block(sd, 'superresolution.block0', x, rgb, ws, noise_mode=nm, clamp=clamp,
                              up=(cfg.sr_module == '8XDC'))
-    x, rgb = synthesis_block(sd, 'superresolution.block1', x, rgb, ws, noise_mode=nm, clamp=256)
+    x, rgb = synthesis_block(sd, 'superresolution.block1', x, rgb, ws, noise_mode=nm, clamp=clamp)
     return rgb
 
 

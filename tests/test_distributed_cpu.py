@@ -46,3 +46,33 @@ def test_gather_two_ranks_gloo():
         assert p.exitcode == 0
     assert ids == [0.0, 1.0, 2.0, 3.0, 4.0, 5.0]        # global sample order preserved
     assert tmax == 11.0
+
+
+def _worker_unequal(rank, world, port, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    r, w, _ = D.init_from_env('gloo')
+    spans = [D.shard_range(5, k, w) for k in range(w)]                          # 5 samples over 2 ranks: 3 + 2
+    a, b = spans[r]
+    imgs = torch.stack([torch.full((3, 2, 2), float(i)) for i in range(a, b)])
+    out = D.gather_images(imgs, dst=0, sizes=[e - s for s, e in spans])
+    if r == 0:
+        q.put(out[:, 0, 0, 0].tolist())
+    torch.distributed.destroy_process_group()
+
+
+def test_gather_unequal_shards_gloo():
+    """total % world != 0: shards differ by one image; the gather pads to the largest and trims on the destination."""
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_unequal, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ids = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ids == [0.0, 1.0, 2.0, 3.0, 4.0]

