@@ -109,6 +109,65 @@ def render_frames(G, ws_frames, cams, verts, batch=8, image_mode='image', noise_
         yield from drain(pending)
 
 
+def render_frames_sharded(G, ws_frames, cams, verts, batch=8, noise_mode='const', seed=0, device=None):
+    """Strong-scaling video driver (BASELINE.json configs[3]: one clip split over the GPUs of a box): rank r renders the contiguous
+    frame range shard_range(F, r, world) in batches through `G.synthesis`, converts to uint8 HWC on the device (4x fewer bytes than
+    the fp32 images) and the batches are gathered to rank 0 over NCCL on a side stream from a ping-pong staging buffer, so batch
+    i+1 renders while batch i is in flight; rank 0 copies every gathered batch to pinned host memory on a third stream.
+    Returns the [F, H, W, 3] uint8 host tensor (frame order) on rank 0, None elsewhere.  World size 1: no collective."""
+    import torch.distributed as dist
+    from . import distributed as D
+    device = device or next(G.parameters()).device
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    F = ws_frames.shape[0]
+    spans = [D.shard_range(F, r, world) for r in range(world)]
+    a, b = spans[rank]
+    steps = max(-(-(e - s) // batch) for s, e in spans)                   # every rank runs the same number of collective steps
+    res = G.img_resolution
+    host = torch.empty(F, res, res, 3, dtype=torch.uint8).pin_memory() if rank == 0 else None
+    main = torch.cuda.current_stream(device)
+    side, copy_s = torch.cuda.Stream(device), torch.cuda.Stream(device)
+    stage = [torch.empty(batch, res, res, 3, dtype=torch.uint8, device=device) for _ in range(2)]
+    gath = [torch.empty(world, batch, res, res, 3, dtype=torch.uint8, device=device) if rank == 0 and world > 1 else None for _ in range(2)]
+    drained = [None, None]
+    static_mesh = verts.shape[0] == 1
+    for k in range(steps):
+        lo = min(a + k * batch, max(b - 1, a))
+        idx = [min(lo + j, b - 1) for j in range(batch)]                   # the tail repeats the last frame (one graph shape)
+        w = ws_frames[idx].to(device, torch.float32, non_blocking=True)
+        c = cams[idx].to(device, torch.float32, non_blocking=True)
+        v = verts.to(device, torch.float32).expand(batch, -1, -1) if static_mesh else verts[idx].to(device, torch.float32, non_blocking=True)
+        img = G.synthesis(w, c, v, noise_mode=noise_mode, seed=int(seed) + rank * steps + k)['image']
+        s = k & 1
+        if drained[s] is not None:
+            main.wait_event(drained[s])                                    # batch k-2 has left this staging buffer
+        stage[s].copy_(to_uint8_hwc(img))
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            if world > 1:
+                dist.gather(stage[s], list(gath[s].unbind(0)) if rank == 0 else None, dst=0)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        drained[s] = ev
+        if rank == 0:
+            copy_s.wait_event(ev)
+            with torch.cuda.stream(copy_s):
+                for r in range(world):
+                    s0, e0 = spans[r]
+                    f0 = s0 + k * batch
+                    n = max(0, min(batch, e0 - f0))
+                    if n > 0:
+                        src = gath[s][r] if world > 1 else stage[s]
+                        host[f0:f0 + n].copy_(src[:n], non_blocking=True)
+                ev2 = torch.cuda.Event()
+                ev2.record(copy_s)
+            drained[s] = ev2                                               # the staging / gather buffers are free once the D2H left them
+    main.wait_stream(side)
+    main.wait_stream(copy_s)
+    return host
+
+
 # ------------------------------------------------------------------------------------------------ shape extraction (row f2)
 def create_samples(N, cube_length, head=0, count=None, device='cpu'):
     """Voxel-grid query points [1, count, 3] of `create_samples` (gen_samples_next3d.py:80-102) for the flat indices
