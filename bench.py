@@ -321,13 +321,14 @@ def _time_c4(G, dev, rank, world, steps, warmup):
         ws = G.mapping(z.to(dev), c_cond.to(dev), truncation_psi=0.7, truncation_cutoff=14)
         wsf = drivers.interpolate_ws(ws.cpu(), F, wraps=2).float()               # one keyframe -> constant w, as in the script
         cams = drivers.orbit_camera_params(F, torch.tensor(G.rendering_kwargs['avg_camera_pivot']), G.rendering_kwargs['avg_camera_radius'])
+        host = torch.empty(F, 512, 512, 3, dtype=torch.uint8).pin_memory() if rank == 0 else None      # the video writer's frame buffer
         for _ in range(max(1, min(warmup, 2))):
-            drivers.render_frames_sharded(G, wsf, cams, v[:1], batch=spec['batch'], seed=1)
+            drivers.render_frames_sharded(G, wsf, cams, v[:1], batch=spec['batch'], seed=1, out=host)
         _barrier(dist, world, dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
-            frames = drivers.render_frames_sharded(G, wsf, cams, v[:1], batch=spec['batch'], seed=100 + i)
+            frames = drivers.render_frames_sharded(G, wsf, cams, v[:1], batch=spec['batch'], seed=100 + i, out=host)
         e1.record()
         _barrier(dist, world, dev)
     dt = D.max_over_ranks(e0.elapsed_time(e1) / 1e3, dev) / steps

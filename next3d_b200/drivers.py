@@ -109,12 +109,15 @@ def render_frames(G, ws_frames, cams, verts, batch=8, image_mode='image', noise_
         yield from drain(pending)
 
 
-def render_frames_sharded(G, ws_frames, cams, verts, batch=8, noise_mode='const', seed=0, device=None):
+def render_frames_sharded(G, ws_frames, cams, verts, batch=8, noise_mode='const', seed=0, device=None, out=None):
     """Strong-scaling video driver (BASELINE.json configs[3]: one clip split over the GPUs of a box): rank r renders the contiguous
     frame range shard_range(F, r, world) in batches through `G.synthesis`, converts to uint8 HWC on the device (4x fewer bytes than
     the fp32 images) and the batches are gathered to rank 0 over NCCL on a side stream from a ping-pong staging buffer, so batch
     i+1 renders while batch i is in flight; rank 0 copies every gathered batch to pinned host memory on a third stream.
-    Returns the [F, H, W, 3] uint8 host tensor (frame order) on rank 0, None elsewhere.  World size 1: no collective."""
+    Returns the [F, H, W, 3] uint8 host tensor (frame order) on rank 0, None elsewhere.  World size 1: no collective.
+    `batch` is an upper bound: the per-call batch is the size in [batch/2, batch] that pads the rank's frame count least (30 frames per
+    rank -> 5 batches of 6, not 4 of 8).  `out`: optional pinned [F, H, W, 3] uint8 host tensor to fill on rank 0 (pinning 190 MB per
+    clip costs tens of milliseconds)."""
     import torch.distributed as dist
     from . import distributed as D
     device = device or next(G.parameters()).device
@@ -123,9 +126,13 @@ def render_frames_sharded(G, ws_frames, cams, verts, batch=8, noise_mode='const'
     F = ws_frames.shape[0]
     spans = [D.shard_range(F, r, world) for r in range(world)]
     a, b = spans[rank]
-    steps = max(-(-(e - s) // batch) for s, e in spans)                   # every rank runs the same number of collective steps
+    nmax = max(e - s for s, e in spans)
+    batch = min(range(max(1, batch // 2), batch + 1), key=lambda bb: (-(-nmax // bb) * bb, -bb))     # least padding, then the largest
+    steps = -(-nmax // batch)                                             # every rank runs the same number of collective steps
     res = G.img_resolution
-    host = torch.empty(F, res, res, 3, dtype=torch.uint8).pin_memory() if rank == 0 else None
+    host = None
+    if rank == 0:
+        host = out if out is not None else torch.empty(F, res, res, 3, dtype=torch.uint8).pin_memory()
     main = torch.cuda.current_stream(device)
     side, copy_s = torch.cuda.Stream(device), torch.cuda.Stream(device)
     stage = [torch.empty(batch, res, res, 3, dtype=torch.uint8, device=device) for _ in range(2)]
