@@ -263,6 +263,19 @@ int n3d_sample_grid(const float* planes, int PH, int PW, int grid_n, float cube_
                     int pad, float pad_value, const float* w0, const float* b0, const float* w1, const float* b1, float* sigma_grid,
                     void* stream);
 
+/* MappingNetwork + truncation in one launch (networks_stylegan2.py:233-268, called through triplane_next3d.py:111-115 with
+ * c[:, :25] * c_scale): z [N,512], c [N,25] -> ws [N,num_ws,512].  embed / fc0 / fc1 are the raw parameters of
+ * `backbone.mapping` (weight [out,in], bias [out]); their runtime gains (1/sqrt(in), lr_multiplier 0.01) are applied inside.
+ * truncation_cutoff < 0 = all layers; w_avg may be NULL when truncation_psi == 1. */
+int n3d_mapping(const float* z, const float* c, int N, float c_scale, const float* embed_w, const float* embed_b, const float* fc0_w,
+                const float* fc0_b, const float* fc1_w, const float* fc1_b, const float* w_avg, float truncation_psi,
+                int truncation_cutoff, int num_ws, float* ws, void* stream);
+
+/* out[f, :] = sum_k B[f, k] * Y[k, :]  (B [F,K], Y [K,D], fp32): the frame drivers' latent interpolation (B = the cubic-spline
+ * basis of gen_videos_next3d.py:106-117 evaluated once on the host) and camera smoothing (reenact_avatar_next3d.py:159) on the
+ * device. */
+int n3d_interp_rows(const float* B, const float* Y, int F, int K, int64_t D, float* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Host-side input parsers (no device work): what the inference scripts do per frame in Python.
  * ---------------------------------------------------------------------------------------------------------- */

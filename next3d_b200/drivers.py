@@ -109,6 +109,63 @@ def render_frames(G, ws_frames, cams, verts, batch=8, image_mode='image', noise_
         yield from drain(pending)
 
 
+# ------------------------------------------------------------------------------------------------ reenactment (reenact_avatar_next3d.py)
+def reenact_schedule(drive_root, num_frames, lms_cond=True):
+    """Frame schedule of reenact_avatar_next3d.py:125-160 for a driving directory (dataset.json + NNN.png / NNN.obj / NNN_kpt2d.txt):
+    the script walks the sorted PNG list, skips k = 0, stops after k = num_frames and smooths the camera over the labels k-1, k, k+1
+    (so the last usable frame is len(labels) - 2; the script itself runs into an IndexError there).
+    -> dict(ks, ids, obj_paths, lms_paths (or None), cams float32 [F, 25])."""
+    import glob
+    import os
+    from . import inputs
+    labels = inputs.load_labels(os.path.join(drive_root, 'dataset.json'))
+    img_list = sorted(glob.glob(drive_root + '/*.png'))
+    ks = [k for k in range(len(img_list)) if 1 <= k <= num_frames and k + 1 < len(labels)]
+    ids = [os.path.basename(img_list[k]).split('.')[0] for k in ks]
+    return dict(ks=ks, ids=ids, obj_paths=[drive_root + f'/{i}.obj' for i in ids],
+                lms_paths=[drive_root + f'/{i}_kpt2d.txt' for i in ids] if lms_cond else None,
+                cams=inputs.smoothed_cameras(labels, ks))
+
+
+def reenact_frames(G, ws, drive_root, num_frames, batch=8, lms_cond=True, fixed_camera=None, noise_mode='const', seed=None,
+                   sampler_noise=None, prefetch_depth=8, workers=4):
+    """reenact_avatar_next3d.py:125-167 for ONE identity `ws` [1, L, D]: yields the rendered uint8 HWC frame of every driving frame,
+    in order.  Meshes are parsed by the native parsers on worker threads (inputs.FramePrefetcher, pinned memory) while the GPU renders
+    batches of `batch` frames; `fixed_camera` [1, 25] replaces the per-frame cameras (the script's --fixed_camera).
+    A `.n3dpack` file written by inputs.write_frame_pack can be given instead of a directory (no parsing at all)."""
+    from . import inputs
+    if str(drive_root).endswith('.n3dpack'):
+        pack = inputs.FramePack(drive_root)
+        n = min(len(pack), num_frames)
+        cams, verts = torch.from_numpy(np.array(pack.cams[:n])), (t for i, t in enumerate(pack) if i < n)
+    else:
+        sch = reenact_schedule(drive_root, num_frames, lms_cond)
+        n = len(sch['ks'])
+        cams = sch['cams']
+        pairs = list(zip(sch['obj_paths'], sch['lms_paths'] if lms_cond else [None] * n))
+        verts = inputs.FramePrefetcher(pairs, depth=prefetch_depth, workers=workers)
+    if fixed_camera is not None:
+        cams = fixed_camera.reshape(1, 25).cpu().float().expand(n, -1)
+    if n == 0:
+        return
+    wsf = ws.detach().cpu().float().reshape(1, *ws.shape[-2:]).expand(n, -1, -1)
+    yield from render_frames(G, wsf, cams, verts, batch=batch, noise_mode=noise_mode, seed=seed, sampler_noise=sampler_noise)
+
+
+def interpolate_ws_device(ws_keyframes, w_frames, wraps=2, kind='cubic'):
+    """interpolate_ws on the device: the spline is linear in its knots, so its basis B [K * w_frames, K] (interp1d evaluated once on
+    the identity, wrap-around tiling folded in) is built on the host and the frames are B @ ws_keyframes in one small kernel
+    (n3d_interp_rows) -- the latents never visit the host.  float32; equals interpolate_ws to ~1e-6."""
+    import scipy.interpolate
+    from . import kernels as K
+    Kf = ws_keyframes.shape[0]
+    x = np.arange(-Kf * wraps, Kf * (wraps + 1))
+    eye = np.tile(np.eye(Kf), [wraps * 2 + 1, 1])                                  # knot i of the tiled sequence is keyframe i % K
+    B = scipy.interpolate.interp1d(x, eye, kind=kind, axis=0)(np.arange(Kf * w_frames) / w_frames)
+    B = torch.from_numpy(B).to(ws_keyframes.device, torch.float32).contiguous()
+    return K.interp_rows(B, ws_keyframes.to(torch.float32).contiguous())
+
+
 def render_frames_sharded(G, ws_frames, cams, verts, batch=8, noise_mode='const', seed=0, device=None, out=None):
     """Strong-scaling video driver (BASELINE.json configs[3]: one clip split over the GPUs of a box): rank r renders the contiguous
     frame range shard_range(F, r, world) in batches through `G.synthesis`, converts to uint8 HWC on the device (4x fewer bytes than

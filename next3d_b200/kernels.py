@@ -230,3 +230,22 @@ def sample_grid(planes, grid_n, cube_length, box_warp, dec, sigma_grid, head=0, 
     count = grid_n ** 3 - head if count is None else count
     check(lib.n3d_sample_grid(ptr(planes), PH, PW, grid_n, float(cube_length), float(box_warp), head, count, pad, float(pad_value),
                               *(ptr(t) for t in dec), ptr(sigma_grid), stream_ptr()), 'n3d_sample_grid')
+
+
+def mapping(z, c, c_scale, m, truncation_psi=1.0, truncation_cutoff=None, num_ws=28):
+    """MappingNetwork + truncation in one launch.  m: dict with embed_w/embed_b/fc0_w/fc0_b/fc1_w/fc1_b/w_avg fp32 device tensors."""
+    N = z.shape[0]
+    ws = torch.empty(N, num_ws, 512, device=z.device, dtype=torch.float32)
+    check(lib.n3d_mapping(ptr(z), ptr(c), N, float(c_scale), ptr(m['embed_w']), ptr(m['embed_b']), ptr(m['fc0_w']), ptr(m['fc0_b']),
+                          ptr(m['fc1_w']), ptr(m['fc1_b']), ptr(m['w_avg']), float(truncation_psi),
+                          -1 if truncation_cutoff is None else int(truncation_cutoff), num_ws, ptr(ws), stream_ptr()), 'n3d_mapping')
+    return ws
+
+
+def interp_rows(B, Y):
+    """out[f] = sum_k B[f,k] * Y[k] for fp32 device tensors B [F,K], Y [K, ...] -> [F, ...]."""
+    F_, K_ = B.shape
+    D = Y[0].numel()
+    out = torch.empty((F_,) + tuple(Y.shape[1:]), device=Y.device, dtype=torch.float32)
+    check(lib.n3d_interp_rows(ptr(B), ptr(Y), F_, K_, D, ptr(out), stream_ptr()), 'n3d_interp_rows')
+    return out

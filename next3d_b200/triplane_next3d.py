@@ -157,6 +157,16 @@ class TriPlaneGenerator(torch.nn.Module):
         m = self.backbone.mapping
         if rk['c_gen_conditioning_zero']:
             c = torch.zeros_like(c)
+        if z.is_cuda:                                   # one fused launch (n3d_mapping); the PyTorch lines below serve CPU tensors only
+            from . import kernels as K
+            tensors = dict(embed_w=m.embed.weight, embed_b=m.embed.bias, fc0_w=m.fc0.weight, fc0_b=m.fc0.bias, fc1_w=m.fc1.weight,
+                           fc1_b=m.fc1.bias, w_avg=m.w_avg)
+            for k, t in tensors.items():
+                if t.device != z.device or t.dtype != torch.float32 or not t.is_contiguous():
+                    raise RuntimeError(f'next3d_b200: mapping parameter {k} must be contiguous float32 on {z.device}')
+            with torch.cuda.device(z.device):
+                return K.mapping(z.to(torch.float32).contiguous(), c[:, :25].to(z.device, torch.float32).contiguous(), rk.get('c_scale', 0),
+                                 tensors, truncation_psi, truncation_cutoff)
         c = c[:, :25] * rk.get('c_scale', 0)
         x = z.to(torch.float32)
         x = x * (x.square().mean(1, keepdim=True) + 1e-8).rsqrt()

@@ -133,3 +133,59 @@ def test_trim_matches_script():
     inner[pad:R - pad, pad:R - pad, pad:R - pad] = True
     ref[~inner] = -1000
     assert np.array_equal(drivers.trim_sigma_grid(sig.clone(), R).numpy(), ref)
+
+
+def _make_drive_root(tmp_path, n=6, with_lms=True):
+    import json
+    rng = np.random.RandomState(0)
+    labels = []
+    for k in range(n):
+        name = f'{k:04d}'
+        (tmp_path / f'{name}.png').write_bytes(b'')
+        v = rng.randn(11, 3)
+        (tmp_path / f'{name}.obj').write_text(''.join(f'v {a:.6f} {b:.6f} {c:.6f}\n' for a, b, c in v) + 'f 1 2 3\n')
+        if with_lms:
+            (tmp_path / f'{name}_kpt2d.txt').write_text('\n'.join(f'{a:.5f} {b:.5f} {c:.5f}' for a, b, c in rng.randn(68, 3)) + '\n')
+        labels.append([f'{name}.png', rng.randn(25).tolist()])
+    (tmp_path / 'dataset.json').write_text(json.dumps({'labels': labels}))
+    return labels
+
+
+def test_reenact_schedule_matches_the_script(tmp_path):
+    """reenact_avatar_next3d.py:125-160 restated with its own expressions: frame selection, file names, smoothed cameras."""
+    import glob
+    import os
+    labels = _make_drive_root(tmp_path, n=6)
+    root = str(tmp_path)
+    num_frames = 4
+    sch = drivers.reenact_schedule(root, num_frames)
+    img_list = sorted(glob.glob(root + '/*.png'))
+    want_ids, want_cams = [], []
+    for k, img_path in enumerate([img for img in img_list]):                      # the script's loop (:125-131, :159-160)
+        if k > num_frames:
+            break
+        if k < 1:
+            continue
+        if k + 1 >= len(labels):
+            continue
+        want_ids.append(os.path.basename(img_list[k]).split('.')[0])
+        camera_params = (np.array(labels[k - 1][1]) + np.array(labels[k][1]) + np.array(labels[k + 1][1])) / 3
+        want_cams.append(torch.tensor(camera_params).unsqueeze(0).float())
+    assert sch['ids'] == want_ids and sch['obj_paths'] == [root + f'/{i}.obj' for i in want_ids]
+    assert sch['lms_paths'] == [root + f'/{i}_kpt2d.txt' for i in want_ids]
+    assert torch.equal(sch['cams'], torch.cat(want_cams))
+
+
+def test_frame_pack_round_trip(tmp_path):
+    from next3d_b200 import inputs
+    _make_drive_root(tmp_path, n=5)
+    root = str(tmp_path)
+    sch = drivers.reenact_schedule(root, 10)
+    verts = np.stack([inputs.load_frame(o, l)[0].numpy() for o, l in zip(sch['obj_paths'], sch['lms_paths'])])
+    path = str(tmp_path / 'clip.n3dpack')
+    inputs.write_frame_pack(path, verts, sch['cams'].numpy(), ids=sch['ids'])
+    pack = inputs.FramePack(path, pin=False)
+    assert len(pack) == len(sch['ids']) and pack.ids == sch['ids']
+    assert np.array_equal(pack.verts, verts) and np.array_equal(pack.cams, sch['cams'].numpy())
+    frames = list(pack)
+    assert frames[1].shape == (1, verts.shape[1], 3) and np.array_equal(frames[1][0].numpy(), verts[1])

@@ -399,7 +399,7 @@ def test_blend(K):
 
 # ------------------------------------------------------------------------------------------------ renderer
 @pytest.mark.parametrize('N,res,D,Df,ties', [(2, 32, 48, 48, 0), (1, 16, 96, 96, 0), (1, 24, 36, 36, 0), (1, 20, 48, 0, 0), (1, 16, 40, 24, 0),
-                                             (2, 12, 12, 70, 0), (3, 64, 48, 48, 0), (1, 16, 48, 48, 1), (1, 12, 96, 96, 1)])
+                                             (2, 12, 12, 70, 0), (3, 64, 48, 48, 0), (1, 16, 48, 48, 1), (1, 12, 96, 96, 1), (1, 12, 96, 96, 0)])
 def test_render_rays(K, N, res, D, Df, ties):
     """Fused renderer vs the oracle with injected sampler noise: both lane layouts (<= 48 / <= 96 samples per pass), ragged tiles,
     image sizes that are not a multiple of the pixel block, coarse-only rendering and unequal coarse / fine resolutions."""
