@@ -131,8 +131,8 @@ def test_reenact_frames_and_pack(tinyG, tmp_path):
         name = f'{k:04d}'
         (tmp_path / f'{name}.png').write_bytes(b'')
         vk = v[0].numpy() + rng.randn(*v[0].shape).astype(np.float32) * 1e-4
-        (tmp_path / f'{name}.obj').write_text(''.join(f'v {a!r} {b!r} {c_!r}\n' for a, b, c_ in vk[:5023].astype(np.float64)))
-        (tmp_path / f'{name}_kpt2d.txt').write_text('\n'.join(f'{a!r} {b!r} {c_!r}' for a, b, c_ in vk[5023:].astype(np.float64)) + '\n')
+        (tmp_path / f'{name}.obj').write_text(''.join(f'v {float(a)!r} {float(b)!r} {float(c_)!r}\n' for a, b, c_ in vk[:5023]))
+        (tmp_path / f'{name}_kpt2d.txt').write_text('\n'.join(f'{float(a)!r} {float(b)!r} {float(c_)!r}' for a, b, c_ in vk[5023:]) + '\n')
         cam = c[0].numpy().astype(np.float64)
         cam[3] += 0.01 * k
         labels.append([f'{name}.png', cam.tolist()])
