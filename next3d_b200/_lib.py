@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libnext3d_b200.so')
+LIB_PATH = os.environ.get('N3D_LIB_PATH') or os.path.join(_HERE, 'libnext3d_b200.so')      # N3D_LIB_PATH: A/B builds of the same library (tools only)
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(f'{LIB_PATH} is missing: build it with `make -C {os.path.join(_HERE, "csrc")}` '

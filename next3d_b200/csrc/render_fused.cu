@@ -397,8 +397,14 @@ __device__ __forceinline__ void epi1_tile(const Smem& S, uint32_t tlane, int ese
         y[c4 * 4] = __uint_as_float(a[c4 * 4]) + bb.x; y[c4 * 4 + 1] = __uint_as_float(a[c4 * 4 + 1]) + bb.y;
         y[c4 * 4 + 2] = __uint_as_float(a[c4 * 4 + 2]) + bb.z; y[c4 * 4 + 3] = __uint_as_float(a[c4 * 4 + 3]) + bb.w;
     }
+    // explicit stages over the 32 independent values: the MUFU operations issue back to back instead of one dependent chain per value
+    float e[32];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) y[c] = fmaxf(lg2_approx(1.f + ex2_approx(fminf(y[c], 126.f))), y[c]);
+    for (int c = 0; c < 32; ++c) e[c] = ex2_approx(fminf(y[c], 126.f));
+#pragma unroll
+    for (int c = 0; c < 32; ++c) e[c] = lg2_approx(1.f + e[c]);
+#pragma unroll
+    for (int c = 0; c < 32; ++c) y[c] = fmaxf(e[c], y[c]);
 #pragma unroll
     for (int c = 0; c < 16; ++c) split_bf16x2(y[2 * c], y[2 * c + 1], hi[c], lo[c]);
     const uint32_t hb = tlane + kColH + 64u * (ti & 1);
@@ -816,7 +822,11 @@ __global__ void __launch_bounds__(kThreads, 1) render_fused_kernel(const __grid_
                     z[c4 * 4 + 2] = __uint_as_float(v[c4 * 4 + 2]) + bb.z; z[c4 * 4 + 3] = __uint_as_float(v[c4 * 4 + 3]) + bb.w;
                 }
 #pragma unroll
-                for (int c = 0; c < 16; ++c) acc[c] = fmaf(coef, rcp_approx(1.f + ex2_approx(z[c])), acc[c]);
+                for (int c = 0; c < 16; ++c) z[c] = ex2_approx(z[c]);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) z[c] = rcp_approx(1.f + z[c]);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) acc[c] = fmaf(coef, z[c], acc[c]);
             };
 #pragma unroll
             for (int t = 0; t < kMaxT; ++t)
