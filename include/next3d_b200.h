@@ -247,6 +247,12 @@ typedef struct {
 } N3DRender;
 
 int n3d_render_rays(const N3DRender* p, void* stream);
+/* Diagnostics: micro-kernels that measure the hard per-SM limits of the renderer's formulation on the workload described by p
+ * (only planes / cameras / res / depth_* / ray_* / box_warp are read; nothing is written but sink[0], which may be NULL):
+ * kind 0 = the tri-plane gather alone (rays, depths, 12 taps per sample, 256-bit loads, weighted sum, bf16 split, shared-memory
+ * tile) on all warps; kind 1 = the decoder's activations alone (192 MUFU operations per sample).  bench.py times them next to
+ * n3d_render_rays to report how far the fused kernel is from what a per-sample gather + MLP can reach. */
+int n3d_render_floor(const N3DRender* p, int kind, float* sink, void* stream);
 /* composite depth clamp to the batch-global depth range (ray_marcher.py:53-54). */
 int n3d_depth_clamp(float* depth, int64_t n, const float* depth_minmax, void* stream);
 /* run_model only (TriPlaneGenerator.sample, triplane_next3d.py:276): coords [N,P,3] -> sigma [N,P], rgb [N,P,32] (or NULL). */

@@ -1151,6 +1151,112 @@ __global__ void __launch_bounds__(kThreads, 1) points_fused_kernel(const __grid_
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------------------------- ceilings
+// Two micro-kernels that isolate the hard per-SM limits of the renderer's formulation on the SAME workload (same rays, same sample
+// positions, same tap arithmetic), used by bench.py / DESIGN.md to say how far render_fused_kernel is from what the hardware
+// allows for a per-sample gather + MLP -- as opposed to the "every texel read once" HBM figure of the survey's formula:
+//   kind 0  gather only : all 16 warps of a CTA run the gather role (ray -> depth -> 12 taps -> 256-bit loads -> weighted sum ->
+//           bf16 split -> shared-memory tile).  No MMA, no epilogue.  Ceiling of the tri-plane fetch (L1 wavefronts + L2 misses).
+//   kind 1  activations only : 192 MUFU operations per sample (64 x (ex2 + lg2), 32 x (ex2 + rcp)) on register operands with the
+//           epilogue's surrounding arithmetic.  Ceiling of the SFU pipe.
+namespace {
+__global__ void __launch_bounds__(kThreads, 1) gather_floor_kernel(const __grid_constant__ FusedK K, float* __restrict__ sink) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* const sb = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const N3DRender& P = K.p;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int L = P.depth_coarse <= 48 ? 16 : 32;
+    uint2* const taps = reinterpret_cast<uint2*>(sb + 32768 + warp * kTapBytesPerWarp);
+    uint8_t* const f_hi = sb, * const f_lo = sb + 8192;          // one shared tile: the stores are part of the cost, the data is not used
+    const int g_begin = (int)((K.total_groups * blockIdx.x) / gridDim.x);
+    const int n_groups = (int)((K.total_groups * (blockIdx.x + 1)) / gridDim.x) - g_begin;
+    const int passes = P.depth_fine > 0 ? 2 : 1;
+    const int T = K.Tc;
+    // item = (group, pass, tile, quarter): the same 32-row work unit the gather warps of the renderer process
+    const int items = n_groups * passes * T * 4;
+    for (int it = warp; it < items; it += kWarps) {
+        const int q = it & 3, t = (it >> 2) % T, pass = (it / (4 * T)) % passes, r = it / (4 * T * passes);
+        const int row = q * 32 + lane, rs = row / L, j = row & (L - 1);
+        const Ray ray = make_ray(K, g_begin + r, rs);
+        const int k = t * L + j;
+        const bool valid = ray.ok && k < P.depth_coarse;
+        // second pass: the fine samples sit near the coarse ones (shifted by half a step) -- same count, same locality
+        const float depth = valid ? coarse_depth(K, P.seed + pass, ray.gr, k) + (pass ? 0.5f * K.delta_coarse : 0.f) : 0.f;
+        setup_taps(taps, lane, ray.ox + depth * ray.dx, ray.oy + depth * ray.dy, ray.oz + depth * ray.dz, valid && !(K.mode & 1), ray.img4, P.PH, P.PW,
+                   K.scale);
+        __syncwarp();
+        gather_rows(P.planes, taps, f_hi, f_lo, q * 32, lane);
+        __syncwarp();
+    }
+    if (sink && threadIdx.x == 0 && blockIdx.x == 0) sink[0] = (float)f_hi[0];
+}
+
+__global__ void __launch_bounds__(kThreads, 1) mufu_floor_kernel(long long samples, float* __restrict__ sink) {
+    // every thread evaluates whole samples: 64 hidden activations (softplus as in epi1) and 32 colour sigmoids
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (long long)gridDim.x * blockDim.x;
+    float acc = 0.f;
+    for (long long s = tid; s < samples; s += nthreads) {
+        float y[32];
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) y[c] = (float)(s & 1023) * 1e-3f + (float)(c + 32 * half) * 0.01f - 0.3f;
+            float e[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) e[c] = ex2_approx(fminf(y[c], 126.f));
+#pragma unroll
+            for (int c = 0; c < 32; ++c) e[c] = lg2_approx(1.f + e[c]);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) acc += fmaxf(e[c], y[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) y[c] = (float)(s & 511) * 2e-3f - (float)c * 0.02f;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) y[c] = ex2_approx(y[c]);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) y[c] = rcp_approx(1.f + y[c]);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc = fmaf(0.5f, y[c], acc);
+    }
+    if (sink && acc == 123.456f) sink[0] = acc;
+}
+}  // namespace
+
+int n3d_render_floor_launch(const N3DRender* p, int kind, float* sink, void* stream) {
+    N3DDeviceState* D = n3d_device_state();
+    if (!D) return N3D_ERR_CUDA;
+    const int dmaxv = p->depth_coarse > p->depth_fine ? p->depth_coarse : p->depth_fine;
+    const int L = dmaxv <= 48 ? 16 : 32;
+    FusedK K;
+    K.p = *p;
+    K.M = p->res * p->res;
+    K.delta_coarse = (float)(((double)p->ray_end - (double)p->ray_start) / (double)(p->depth_coarse - 1));
+    K.scale = 2.f / p->box_warp;
+    K.Tc = (p->depth_coarse + L - 1) / L;
+    K.Tf = (p->depth_fine + L - 1) / L;
+    K.gw = L == 16 ? 4 : 2;
+    K.log2gw = L == 16 ? 2 : 1;
+    const int tiles_x = (p->res + K.gw - 1) / K.gw, tiles_y = (p->res + 1) / 2;
+    K.blocks_x = (tiles_x + 3) / 4;
+    K.gpi = K.blocks_x * ((tiles_y + 7) / 8) * 32;
+    K.total_groups = (long long)p->N * K.gpi;
+    K.mode = 0;
+    const int grid = (int)(K.total_groups < D->num_sms ? K.total_groups : D->num_sms);
+    if (kind == 0) {
+        const size_t smem = 32768 + kWarps * kTapBytesPerWarp + 1024;
+        if (cudaFuncSetAttribute(gather_floor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            n3d_set_error("n3d_render_floor: cannot raise dynamic shared memory");
+            return N3D_ERR_CUDA;
+        }
+        gather_floor_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(K, sink);
+    } else {
+        const long long samples = (long long)p->N * K.M * (p->depth_coarse + p->depth_fine);
+        mufu_floor_kernel<<<D->num_sms, kThreads, 0, (cudaStream_t)stream>>>(samples, sink);
+    }
+    N3D_CHECK_LAUNCH("n3d_render_floor");
+    return N3D_OK;
+}
+
 int n3d_render_fused_launch(const N3DRender* p, void* stream, int mode) {
     const int dmaxv = p->depth_coarse > p->depth_fine ? p->depth_coarse : p->depth_fine;
     const int L = dmaxv <= 48 ? 16 : 32;

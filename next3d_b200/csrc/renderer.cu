@@ -18,6 +18,7 @@ __global__ void __launch_bounds__(256) depth_clamp_kernel(float* __restrict__ de
 }  // namespace
 
 int n3d_render_fused_launch(const N3DRender* p, void* stream, int mode);     // render_fused.cu
+int n3d_render_floor_launch(const N3DRender* p, int kind, float* sink, void* stream);
 int n3d_points_fused_launch(const float* planes, int N, int PH, int PW, const float* coords, long long Pn, float box_warp, const float* w0,
                             const float* b0, const float* w1, const float* b1, float* sigma, float* rgb, int grid_n, float cube_length, long long head,
                             int pad, float pad_value, void* stream);
@@ -62,4 +63,10 @@ extern "C" int n3d_sample_grid(const float* planes, int PH, int PW, int grid_n, 
     N3D_CHECK_ARG((long long)3 * PH * PW * 128 < (1ll << 32), "n3d_sample_grid: plane tensor too large for 32-bit texel offsets");
     return n3d_points_fused_launch(planes, 1, PH, PW, nullptr, count, box_warp, w0, b0, w1, b1, sigma_grid, nullptr, grid_n, cube_length, head, pad,
                                    pad_value, stream);
+}
+
+extern "C" int n3d_render_floor(const N3DRender* p, int kind, float* sink, void* stream) {
+    N3D_CHECK_ARG(p && p->planes && p->cam2world && p->intrinsics && (kind == 0 || kind == 1), "n3d_render_floor: bad args");
+    N3D_CHECK_ARG(p->depth_coarse >= 4 && p->depth_coarse <= kMaxD && p->depth_fine >= 0 && p->depth_fine <= kMaxD, "n3d_render_floor: depth resolutions");
+    return n3d_render_floor_launch(p, kind, sink, stream);
 }

@@ -249,3 +249,15 @@ def interp_rows(B, Y):
     out = torch.empty((F_,) + tuple(Y.shape[1:]), device=Y.device, dtype=torch.float32)
     check(lib.n3d_interp_rows(ptr(B), ptr(Y), F_, K_, D, ptr(out), stream_ptr()), 'n3d_interp_rows')
     return out
+
+
+def render_floor(planes, cam2world, intrinsics, res, opts, kind, seed=0):
+    """Diagnostics (n3d_render_floor): launch the gather-only (kind 0) or activations-only (kind 1) micro-kernel on the renderer's workload."""
+    p = _lib.Render()
+    N, _, PH, PW, _ = planes.shape
+    p.planes, p.N, p.PH, p.PW = ptr(planes), N, PH, PW
+    p.cam2world, p.intrinsics, p.res = ptr(cam2world), ptr(intrinsics), res
+    p.depth_coarse, p.depth_fine = opts['depth_resolution'], opts['depth_resolution_importance']
+    p.ray_start, p.ray_end, p.box_warp = float(opts['ray_start']), float(opts['ray_end']), float(opts['box_warp'])
+    p.seed = seed
+    check(lib.n3d_render_floor(C.byref(p), int(kind), None, stream_ptr()), 'n3d_render_floor')
