@@ -3,8 +3,7 @@
 # ncu --set full captures of every kernel family.  Outputs land in gpurun_out/; tools/launch_table.py, tools/dram_table.py and
 # tools/summarize_ncu.py turn them into the files committed under profiles/.
 R=${1:-r02}
-rm -f gpurun_out/parity_report.jsonl
-timeout 1500 python -m pytest tests/ -m gpu -q 2>&1 | tail -3
+if [ "$2" != "notests" ]; then rm -f gpurun_out/parity_report.jsonl; timeout 1500 python -m pytest tests/ -m gpu -q 2>&1 | tail -3; fi
 python bench.py > gpurun_out/bench_$R.json 2> gpurun_out/bench_$R.err
 tail -2 gpurun_out/bench_$R.err
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference_$R.json 2>/dev/null
@@ -18,8 +17,11 @@ N3D_BENCH_GRID=0 ncu --set full --clock-control none --import-source on -k regex
 ncu --set full --clock-control none --import-source on -k regex:points_fused -s 2 -c 1 -f -o gpurun_out/prof_points_$R python tools/bench_render.py c2 > /dev/null 2>&1
 ncu --set full --clock-control none -k "regex:^(rasterize|raster_setup|uv_sample|fill_mouth|resize_aa|transform|blend|mouth_box|fir_up|fir_down|upsample2d|downsample2d|styles|demod|modulate_split|mapping|depth_clamp)" \
     -s 120 -c 45 -f -o gpurun_out/prof_glue_$R python bench.py --no-graph --steps 1 --warmup 3 --no-cpu-baseline --no-other-configs > /dev/null 2>&1
+python tools/summarize_ncu.py gpurun_out/prof_glue_$R.ncu-rep > gpurun_out/ncu_glue_$R.txt 2>&1; rm -f gpurun_out/prof_glue_$R.ncu-rep      # gpurun_out/ must stay below 64 MiB
 ncu --set full --clock-control none -k "regex:(upfirdn2d_kernel|bias_act_kernel|flrelu)" -c 8 -f -o gpurun_out/prof_ops_$R python -m pytest tests/test_gpu_ops_api.py -q -m gpu > /dev/null 2>&1
+python tools/summarize_ncu.py gpurun_out/prof_ops_$R.ncu-rep > gpurun_out/ncu_ops_$R.txt 2>&1; rm -f gpurun_out/prof_ops_$R.ncu-rep
 cap() { ncu --set full --clock-control none --import-source on -k "regex:$1" -s $2 -c 1 -f -o gpurun_out/prof_$3_$R python bench.py --no-graph --steps 1 --warmup 3 --no-cpu-baseline --no-other-configs > /dev/null 2>&1; }
 cap conv_gemm 395 convsr
 cap conv_gemm 314 convT
-ls -la gpurun_out/*_$R.ncu-rep
+for k in render render_c3 points convsr convT; do python tools/summarize_ncu.py gpurun_out/prof_${k}_$R.ncu-rep > gpurun_out/ncu_${k}_$R.txt 2>&1; done
+ls -la gpurun_out/*_$R.ncu-rep; du -sh gpurun_out
