@@ -87,9 +87,10 @@ def _traffic(kernel):
         path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', fname)
         try:
             with open(path) as f:
-                k = json.load(f)['kernels'][kernel]
+                ks = json.load(f)['kernels']
+            k = ks[kernel] if kernel in ks else next(v for n, v in ks.items() if n.startswith(kernel + '<'))     # template instances
             return k['dram_bytes_per_launch'], 'profiles/%s (ncu, %d launches of one batch-8 forward)' % (fname, k['launches'])
-        except (OSError, KeyError, ValueError):
+        except (OSError, KeyError, ValueError, StopIteration):
             continue
     return None, None
 

@@ -9,25 +9,25 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_launch_table_matches_committed_summary():
-    out = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'launch_table.py'), os.path.join(ROOT, 'profiles', 'r01_launches.csv')],
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'launch_table.py'), os.path.join(ROOT, 'profiles', 'r02_launches.csv')],
                          capture_output=True, text=True, check=True).stdout
     rows = {l.split()[0]: l.split() for l in out.splitlines() if len(l.split()) == 4 and l.split()[1].isdigit()}
     assert int(rows['conv_gemm_kernel'][1]) == 99                      # conv launches of one forward
     assert sum(int(r[1]) for r in rows.values()) == 185                 # all launches of one forward
-    committed = open(os.path.join(ROOT, 'profiles', 'r01_launches_summary.txt')).read()
+    committed = open(os.path.join(ROOT, 'profiles', 'r02_launches_summary.txt')).read()
     assert rows['conv_gemm_kernel'][2] in committed                     # same total time as the committed summary
 
 
 def test_dram_table_and_bench_lookup(tmp_path):
     dst = tmp_path / 'dram.json'
-    subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'dram_table.py'), os.path.join(ROOT, 'profiles', 'r01_launches.csv'), str(dst)],
+    subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'dram_table.py'), os.path.join(ROOT, 'profiles', 'r02_launches.csv'), str(dst)],
                    capture_output=True, text=True, check=True)
     got = json.load(open(dst))['kernels']
-    ref = json.load(open(os.path.join(ROOT, 'profiles', 'r01_dram_traffic.json')))['kernels']
+    ref = json.load(open(os.path.join(ROOT, 'profiles', 'r02_dram_traffic.json')))['kernels']
     assert got['conv_gemm_kernel']['launches'] == ref['conv_gemm_kernel']['launches'] == 99
     assert abs(got['conv_gemm_kernel']['dram_bytes_per_launch'] - ref['conv_gemm_kernel']['dram_bytes_per_launch']) < 1.0
     sys.path.insert(0, ROOT)
     import bench
     tr, src = bench._traffic('conv_gemm_kernel')
-    assert tr == ref['conv_gemm_kernel']['dram_bytes_per_launch'] and 'r01_dram_traffic.json' in src
+    assert tr == ref['conv_gemm_kernel']['dram_bytes_per_launch'] and 'r02_dram_traffic.json' in src
     assert bench._traffic('no_such_kernel') == (None, None)

@@ -16,8 +16,13 @@ def main(src, dst):
     per = collections.defaultdict(dict)
     for r in rows[1:]:
         per[(int(r[ii]), r[ki].split('(')[0].replace('<unnamed>::', '').replace('void ', ''))][r[mi]] = float(r[vi].replace(',', '')) * UNIT.get(r[ui], 1.0)
+    keys = sorted(per.keys())
+    starts = [i for i, (_, n) in enumerate(keys) if n == 'styles_kernel']        # one full generator step, like tools/launch_table.py
+    if len(starts) >= 2:
+        keys = keys[starts[0]:starts[1]]
     out = collections.OrderedDict()
-    for (_, name), m in sorted(per.items()):
+    for (lid, name) in keys:
+        m = per[(lid, name)]
         o = out.setdefault(name, dict(launches=0, dram_read_bytes=0.0, dram_write_bytes=0.0, time_us=0.0))
         o['launches'] += 1
         o['dram_read_bytes'] += m.get('dram__bytes_read.sum', 0.0)
