@@ -115,7 +115,9 @@ typedef struct {
  * over an M-space of N x MH x MW "tile pixels"; out-of-range A reads are zero (this is the conv padding).
  * Epilogue (mode 0): v = acc * dcoef[n,o] + noise[oy,ox] + bias[o]; v = lrelu_slope(v) * gain; clamp; then any of
  *   out[k].hi/lo <- split_bf16(v * out[k].style[n,o]),  out_f32 <- v (optionally += existing, NHWC or NCHW).
- * Epilogue (mode 1): out_f32 <- acc (raw), used by the transposed-conv parity classes.
+ * Epilogue (mode 1): out_f32 <- acc (raw), used by the transposed-conv parity classes and by split-K.
+ * Split-K (splits > 1): for launches with a handful of tiles and a long K loop (the 4^2 / 8^2 layers: one 128-row tile, K = 9 * 512)
+ * the taps x channel-chunks are cut into `splits` slices that run as independent work items; deterministic (no atomics).
  * Output pixel of tile pixel (y, x) is (y*oy_mul + oy_off, x*ox_mul + ox_off) in an OH x OW image. */
 typedef struct {
     const void* a_hi; const void* a_lo;      /* bf16 NHWC [NI, AH, AW, Cin] */
@@ -136,6 +138,8 @@ typedef struct {
     float* out_f32; int32_t f32_cstride, f32_coff, f32_nchw, f32_accumulate;
     int32_t oy_mul, oy_off, ox_mul, ox_off, OH, OW;
     N3DFusedRgb rgb;
+    int32_t splits;                          /* > 1: split-K (mode 1 only): K slice s of every tile writes its raw partial sums to */
+    int64_t split_stride;                    /*      out_f32 + s * split_stride (elements); reduce with n3d_splitk_epilogue */
 } N3DConvGemm;
 
 int n3d_conv_gemm(const N3DConvGemm* p, void* stream);
@@ -154,9 +158,15 @@ int n3d_modulate_split(const float* x, int64_t npix_per_img, int N, int C, const
 
 /* Second half of an up-sampling modulated conv (conv2d_resample.py:114-131 + networks_stylegan2.py:320-329):
  * raw [(2H+1),(2W+1)] transposed-conv output (fp32 NHWC) -> 4x4 FIR [1,3,3,1]^2/64 * 4, pad 1 -> [2H,2W], then the
- * same epilogue as n3d_conv_gemm mode 0. */
+ * same epilogue as n3d_conv_gemm mode 0 (requires gain > 0 and 0 <= slope <= 1: lrelu / linear). */
 int n3d_fir_up_epilogue(const float* raw, int N, int H2, int W2, int C, const float* dcoef, const float* bias,
                         const float* noise, int64_t noise_nstride, float gain, float slope, float clamp,
+                        const N3DSplitOut out[2], float* out_f32, int f32_cstride, int f32_coff, void* stream);
+
+/* Second pass of a split-K convolution: y = sum_s partial[s] (fixed order) followed by the mode-0 epilogue of n3d_conv_gemm
+ * (demod, noise, bias, lrelu * gain, clamp, modulated split-bf16 copies, fp32 copy).  partial: fp32 NHWC [S][N,H,W,C]. */
+int n3d_splitk_epilogue(const float* partial, int S, int64_t split_stride, int N, int H, int W, int C, const float* dcoef,
+                        const float* bias, const float* noise, int64_t noise_nstride, float gain, float slope, float clamp,
                         const N3DSplitOut out[2], float* out_f32, int f32_cstride, int f32_coff, void* stream);
 
 /* First half of a down-sampling conv (conv2d_resample.py:108-111): fp32 NHWC [H,W] -> FIR pad (2,2,2,2) -> [(H+1),(W+1)]

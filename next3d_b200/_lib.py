@@ -47,6 +47,7 @@ class ConvGemm(C.Structure):
         ('out_f32', P), ('f32_cstride', I32), ('f32_coff', I32), ('f32_nchw', I32), ('f32_accumulate', I32),
         ('oy_mul', I32), ('oy_off', I32), ('ox_mul', I32), ('ox_off', I32), ('OH', I32), ('OW', I32),
         ('rgb', FusedRgb),
+        ('splits', I32), ('split_stride', I64),
     ]
 
 
@@ -75,6 +76,7 @@ _SIGNATURES = {
     'n3d_fir_up_epilogue': ([P, C.c_int, C.c_int, C.c_int, C.c_int, P, P, P, I64, F32, F32, F32, C.POINTER(SplitOut), P, C.c_int, C.c_int, P], C.c_int),
     'n3d_parse_obj_vertices': ([C.c_char_p, I64, P, I64, C.POINTER(I64)], C.c_int),
     'n3d_parse_float_table': ([C.c_char_p, I64, P, I64, C.POINTER(I64), C.POINTER(I64)], C.c_int),
+    'n3d_splitk_epilogue': ([P, C.c_int, I64, C.c_int, C.c_int, C.c_int, C.c_int, P, P, P, I64, F32, F32, F32, C.POINTER(SplitOut), P, C.c_int, C.c_int, P], C.c_int),
     'n3d_fir_down_split': ([P, C.c_int, C.c_int, C.c_int, C.c_int, P, P, P], C.c_int),
     'n3d_upsample2d_nhwc': ([P, C.c_int, C.c_int, C.c_int, C.c_int, P, C.c_int, P], C.c_int),
     'n3d_downsample2d_nhwc': ([P, C.c_int, C.c_int, C.c_int, C.c_int, P, P], C.c_int),

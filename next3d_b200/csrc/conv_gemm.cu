@@ -38,6 +38,7 @@ struct KParams {
     // up to 4 sub-problems sharing operands / tile shape / epilogue (the 4 output-parity classes of a stride-2 transposed conv)
     int nsub;
     struct Sub { int tap_begin, ntaps, MH, MW, tiles_x, tiles_y, oy_off, ox_off, tile_end; } sub[4];
+    int splits; long long split_stride;   // split-K: work item = (tile, K slice); slice s writes its raw partial sums to out_f32 + s * split_stride
     int pair, tile_h, acc_half;        // pair = 1: a CTA tile is two vertically stacked 128-row sub-tiles (M = 256) sharing one weight tile
     int block_n, acc_stride, tmem_cols, stages, stage_bytes, b_bytes, a_bytes, block_k;
     int cin_chunks, ntaps, nprod, a_img_stride;
@@ -54,11 +55,13 @@ struct KParams {
 
 __device__ __forceinline__ int staged_rgb_channels(const KParams& P) { return (P.rgb.out && P.TN == 1 && P.mode == 0 && P.tiles_n == 1) ? P.rgb.channels : 0; }
 
-struct TileInfo { int sub, tn, x0, y0, n0; };
+struct TileInfo { int sub, tn, x0, y0, n0, split; };
 // Tiles are numbered sub-problem-major (all tiles of parity class 0, then class 1, ...), n-tile minor.  Interleaving the classes
 // of one spatial tile across neighbouring CTAs (better L2 re-use of the shared activation tile) was measured 0-35 % slower on
 // B200: the kernel is bound by L2->SM fill bandwidth, not DRAM, and the interleaved schedule balances the 4/2/2/1-tap classes worse.
 __device__ __forceinline__ TileInfo decode_tile(const KParams& P, int tile) {
+    const int split = tile % P.splits;                         // K slices of one tile are neighbouring work items (run concurrently)
+    tile /= P.splits;
     int sidx = 0, begin = 0;
     while (sidx + 1 < P.nsub && tile >= P.sub[sidx].tile_end) { begin = P.sub[sidx].tile_end; ++sidx; }
     const int local = tile - begin;
@@ -69,7 +72,15 @@ __device__ __forceinline__ TileInfo decode_tile(const KParams& P, int tile) {
     t.x0 = (tm % tx) * P.TW;
     t.y0 = ((tm / tx) % ty) * P.tile_h;
     t.n0 = (tm / (tx * ty)) * P.TN;
+    t.split = split;
     return t;
+}
+
+// K-step range [kb, ke) of a work item: all taps x channel chunks, or the item's slice of them under split-K.
+__device__ __forceinline__ void k_range(const KParams& P, const TileInfo& t, int& kb, int& ke) {
+    const int nsteps = P.sub[t.sub].ntaps * P.cin_chunks, per = (nsteps + P.splits - 1) / P.splits;
+    kb = t.split * per;
+    ke = min(nsteps, kb + per);
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
@@ -107,7 +118,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-    const int total_tiles = P.sub[P.nsub - 1].tile_end;
+    const int total_tiles = P.sub[P.nsub - 1].tile_end * P.splits;
 
     if (warp == 0) {
         // ===================================================== TMA producer
@@ -117,23 +128,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const TileInfo ti = decode_tile(P, tile);
                 const int tn = ti.tn, x0 = ti.x0, y0 = ti.y0, n0 = ti.n0;
-                const int tap_begin = P.sub[ti.sub].tap_begin, ntaps = P.sub[ti.sub].ntaps;
-                for (int t = 0; t < ntaps; ++t) {
+                const int tap_begin = P.sub[ti.sub].tap_begin;
+                int kb, ke;
+                k_range(P, ti, kb, ke);
+                for (int idx = kb; idx < ke; ++idx) {
+                    const int t = idx / P.cin_chunks, kc = idx - t * P.cin_chunks;
                     const N3DConvTap tap = P.taps[tap_begin + t];
-                    for (int kc = 0; kc < P.cin_chunks; ++kc) {
-                        mbar_wait(empty_bar(s), ph ^ 1u, P.err_flag, 1);
-                        const uint32_t sa = smem_base + (uint32_t)s * (uint32_t)P.stage_bytes;
-                        const uint32_t fb = full_bar(s);
-                        mbar_expect_tx(fb, tx_bytes);
-                        const int img = n0 + (int)tap.img_off * P.a_img_stride;
-                        tma_load_4d(sa, &P.tmA_hi, fb, kc * P.block_k, x0 + tap.dx, y0 + tap.dy, img);
-                        tma_load_3d(sa + 2 * P.a_bytes, &P.tmB_hi, fb, kc * P.block_k, tn * P.block_n, tap.wtap);
-                        if (P.nprod == 3) {
-                            tma_load_4d(sa + P.a_bytes, &P.tmA_lo, fb, kc * P.block_k, x0 + tap.dx, y0 + tap.dy, img);
-                            tma_load_3d(sa + 2 * P.a_bytes + P.b_bytes, &P.tmB_lo, fb, kc * P.block_k, tn * P.block_n, tap.wtap);
-                        }
-                        if (++s == P.stages) { s = 0; ph ^= 1u; }
+                    mbar_wait(empty_bar(s), ph ^ 1u, P.err_flag, 1);
+                    const uint32_t sa = smem_base + (uint32_t)s * (uint32_t)P.stage_bytes;
+                    const uint32_t fb = full_bar(s);
+                    mbar_expect_tx(fb, tx_bytes);
+                    const int img = n0 + (int)tap.img_off * P.a_img_stride;
+                    tma_load_4d(sa, &P.tmA_hi, fb, kc * P.block_k, x0 + tap.dx, y0 + tap.dy, img);
+                    tma_load_3d(sa + 2 * P.a_bytes, &P.tmB_hi, fb, kc * P.block_k, tn * P.block_n, tap.wtap);
+                    if (P.nprod == 3) {
+                        tma_load_4d(sa + P.a_bytes, &P.tmA_lo, fb, kc * P.block_k, x0 + tap.dx, y0 + tap.dy, img);
+                        tma_load_3d(sa + 2 * P.a_bytes + P.b_bytes, &P.tmB_lo, fb, kc * P.block_k, tn * P.block_n, tap.wtap);
                     }
+                    if (++s == P.stages) { s = 0; ph ^= 1u; }
                 }
             }
         }
@@ -147,8 +159,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             const int k16 = P.block_k / 16;
             int s = 0; uint32_t ph = 0; int cnt = 0;            // cnt: tiles of this CTA so far -> accumulator buffer (parity) + barrier phase
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int sub = decode_tile(P, tile).sub;
-                const int ksteps = P.sub[sub].ntaps * P.cin_chunks;
+                int kb, ke;
+                k_range(P, decode_tile(P, tile), kb, ke);
+                const int ksteps = ke - kb;
                 const int acc = cnt & 1;
                 const uint32_t acc_ph = (uint32_t)(cnt >> 1) & 1u;
                 ++cnt;
@@ -303,7 +316,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 #pragma unroll
                         for (int j = 0; j < 16; ++j) if (j < nco) dst[j * cs] = v[j];
                     } else {
-                        float* dst = P.out_f32 + opix * P.f32_cstride + P.f32_coff + co0;
+                        float* dst = P.out_f32 + (int64_t)ti.split * P.split_stride + opix * P.f32_cstride + P.f32_coff + co0;
                         if (nco == 16 && (((uintptr_t)dst & 31) == 0)) {                 // two full 32-byte sectors per thread
                             if (P.f32_accumulate) {
                                 float old[16];
@@ -439,11 +452,15 @@ int launch_conv(const N3DConvGemm* p, int nsub, const SubSpec* specs, void* stre
     N3D_CHECK_ARG(p->Cout >= 1 && p->N >= 1, "n3d_conv_gemm: bad sizes");
     N3D_CHECK_ARG(((uintptr_t)p->a_hi & 15) == 0 && ((uintptr_t)p->w_hi & 15) == 0, "n3d_conv_gemm: operands must be 16-byte aligned");
     N3D_CHECK_ARG(p->mode == 0 || (p->mode == 1 && p->out_f32), "n3d_conv_gemm: bad mode");
+    const int splits = p->splits > 1 ? p->splits : 1;
+    N3D_CHECK_ARG(splits == 1 || (p->mode == 1 && nsub == 1 && !p->f32_nchw && !p->f32_accumulate && p->split_stride > 0),
+                  "n3d_conv_gemm: split-K needs mode 1 (raw NHWC fp32 partial sums) and a split stride");
     cudaStream_t st = (cudaStream_t)stream;
 
     KParams K;
     memset(&K, 0, sizeof(K));
     K.N = p->N; K.Cout = p->Cout;
+    K.splits = splits; K.split_stride = p->split_stride;
     int maxH = 1, maxW = 1;
     for (int i = 0; i < nsub; ++i) { maxH = max(maxH, specs[i].MH); maxW = max(maxW, specs[i].MW); }
     K.TW = min(16, pow2_ceil(maxW));
@@ -478,7 +495,7 @@ int launch_conv(const N3DConvGemm* p, int nsub, const SubSpec* specs, void* stre
             bn = cands[i];
             break;
         }
-        while (bn > 32 && tiles_m * n3d_div_up(p->Cout, bn) < kMinTiles) bn = (bn == 96) ? 32 : bn / 2;
+        while (bn > 32 && tiles_m * splits * n3d_div_up(p->Cout, bn) < kMinTiles) bn = (bn == 96) ? 32 : bn / 2;
         if (p->rgb.out) {                                   // fused ToRGB needs every output channel of a pixel in one tile
             N3D_CHECK_ARG(cout16 <= 256 && cout16 % 16 == 0, "n3d_conv_gemm: fused ToRGB needs Cout <= 256");
             N3D_CHECK_ARG(p->rgb.channels >= 1 && p->rgb.channels <= 4 && p->rgb.weight && p->rgb.style && p->rgb.bias, "n3d_conv_gemm: bad fused ToRGB descriptor");
@@ -491,7 +508,7 @@ int launch_conv(const N3DConvGemm* p, int nsub, const SubSpec* specs, void* stre
     // Pair mode (M = 256 per CTA tile): with block_n = 128 the kernel is bound by the L2 -> shared-memory fill rate (measured
     // 12.3 TB/s chip-wide, profiles/r01_ncu_convsr.txt), not by the tensor pipe; two sub-tiles sharing each weight tile cut the
     // bytes per MMA by 25 %.  Only for launches with several waves of tiles.
-    K.pair = (bn == 128 && K.TN == 1 && tiles_m * K.tiles_n >= 8 * 148) ? 1 : 0;
+    K.pair = (bn == 128 && K.TN == 1 && splits == 1 && tiles_m * K.tiles_n >= 8 * 148) ? 1 : 0;
     {
         static int force = -2;
         if (force == -2) { const char* e = getenv("N3D_CONV_PAIR"); force = e ? atoi(e) : -1; }
@@ -511,6 +528,10 @@ int launch_conv(const N3DConvGemm* p, int nsub, const SubSpec* specs, void* stre
     K.stage_bytes = 2 * K.a_bytes + 2 * K.b_bytes;
     K.stages = min(6, (200 * 1024) / K.stage_bytes);      // + 16 KiB epilogue staging + barriers + 1 KiB alignment slack <= 227 KiB
     K.cin_chunks = n3d_div_up(p->Cin, K.block_k);
+    if (splits > 1) {                                        // every K slice must own at least one step
+        const int nsteps = tap_total * K.cin_chunks, per = n3d_div_up(nsteps, splits);
+        N3D_CHECK_ARG(per * (splits - 1) < nsteps, "n3d_conv_gemm: %d K slices for %d K steps", splits, nsteps);
+    }
     K.ntaps = tap_total; K.nprod = p->nprod; K.a_img_stride = p->a_img_mul;
     {
         int end = 0;
@@ -547,7 +568,7 @@ int launch_conv(const N3DConvGemm* p, int nsub, const SubSpec* specs, void* stre
         }
         D->configured |= N3D_CFG_CONV;
     }
-    const int total_tiles = tiles_m * K.tiles_n;
+    const int total_tiles = tiles_m * K.tiles_n * splits;
     const int num_sms = D->num_sms;
     const int grid = min(total_tiles, num_sms);
     conv_gemm_kernel<<<grid, kThreads, smem, st>>>(K);

@@ -250,6 +250,28 @@ __global__ void __launch_bounds__(256) fir_up_epilogue_kernel(const float* __res
     }
 }
 
+// Second pass of a split-K convolution: sum the S raw partial tensors in a fixed order, then the usual epilogue.
+// thread = (pixel, 4-channel group).
+__global__ void __launch_bounds__(256) splitk_epilogue_kernel(const float* __restrict__ part, int S, int64_t stride, int N, int H, int W, int C, EpiParams E) {
+    const int c4n = C >> 2;
+    const int64_t total = (int64_t)N * H * W * c4n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i % c4n);
+        const int64_t pix = i / c4n;
+        const int n = (int)(pix / ((int64_t)H * W));
+        const int64_t yx = pix - (int64_t)n * H * W;
+        float4 acc = __ldg(reinterpret_cast<const float4*>(part) + i);
+        for (int s = 1; s < S; ++s) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(part + (int64_t)s * stride) + i);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        const EpiVec V = epi_load(E, n, C, c4 * 4);
+        const EpiCursor P = epi_cursor(E, pix, c4 * 4);
+        const float nzg = E.noise ? E.gain * __ldg(E.noise + (int64_t)n * E.noise_nstride + yx) : 0.f;
+        epi_store(E, V, P, acc, nzg, 0);
+    }
+}
+
 // Same for the down path, where the window starts two columns left of x0 (input columns x0-2 .. x0+2, x0 even in [0, W]): the
 // first two are outside together (x0 == 0: vl), the next two together (x0 == W: vm), the last one when x0 + 2 >= W (vr).
 __device__ __forceinline__ void fir_hrow_down(const float4* __restrict__ p, int cs, bool vl, bool vm, bool vr, const float (&g)[4], float4& h0, float4& h1) {
@@ -455,6 +477,24 @@ extern "C" int n3d_fir_up_epilogue(const float* raw, int N, int H2, int W2, int 
     // 2 output columns per thread: measured best on B200 (1 column: +23 % time despite 1.5x the occupancy, 4 columns: +15 %)
     fir_up_epilogue_kernel<2><<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(raw, N, H2, W2, C, S, E);
     N3D_CHECK_LAUNCH("n3d_fir_up_epilogue");
+    return N3D_OK;
+}
+
+extern "C" int n3d_splitk_epilogue(const float* partial, int S, int64_t split_stride, int N, int H, int W, int C, const float* dcoef,
+                                   const float* bias, const float* noise, int64_t noise_nstride, float gain, float slope, float clamp,
+                                   const N3DSplitOut out[2], float* out_f32, int f32_cstride, int f32_coff, void* stream) {
+    N3D_CHECK_ARG(partial && out && S >= 1 && N > 0 && H > 0 && W > 0, "n3d_splitk_epilogue: bad args");
+    N3D_CHECK_ARG(C % 4 == 0 && split_stride % 4 == 0 && ((uintptr_t)partial & 15) == 0, "n3d_splitk_epilogue: C and the split stride must be multiples of 4");
+    N3D_CHECK_ARG(gain > 0.f && slope >= 0.f && slope <= 1.f, "n3d_splitk_epilogue: needs gain > 0 and 0 <= slope <= 1 (lrelu / linear)");
+    EpiParams E;
+    E.dcoef = dcoef; E.bias = bias; E.noise = noise; E.noise_nstride = noise_nstride; E.gain = gain; E.slope = slope; E.clamp = clamp;
+    E.out[0] = out[0]; E.out[1] = out[1]; E.out_f32 = out_f32; E.f32_cstride = f32_cstride; E.f32_coff = f32_coff;
+    for (int k = 0; k < 2; ++k)
+        N3D_CHECK_ARG(!E.out[k].hi || ((E.out[k].cstride % 4 == 0) && (E.out[k].coff % 4 == 0)), "n3d_splitk_epilogue: unaligned split output");
+    N3D_CHECK_ARG(!out_f32 || (f32_cstride % 4 == 0 && f32_coff % 4 == 0), "n3d_splitk_epilogue: unaligned fp32 output");
+    const int64_t total = (int64_t)N * H * W * (C / 4);
+    splitk_epilogue_kernel<<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(partial, S, split_stride, N, H, W, C, E);
+    N3D_CHECK_LAUNCH("n3d_splitk_epilogue");
     return N3D_OK;
 }
 

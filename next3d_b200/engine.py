@@ -85,6 +85,7 @@ class Engine:
         self._graphs = {}
         self._side = None                       # side streams of the concurrent branches (compute_planes)
         self.concurrent = os.environ.get('N3D_CONCURRENT', '1') != '0'
+        self.splitk = os.environ.get('N3D_SPLITK', '1') != '0'
 
     # ------------------------------------------------------------------------------------------ packing (one-time)
     def _add_mod(self, sd, name, cin, cout, k, up, widx, is_rgb=False, clamp=None, noise=True):
@@ -269,12 +270,30 @@ class Engine:
         return dict(out=img, weight=L.w_f32, style=self._style(L), bias=L.bias, clamp=L.clamp if L.clamp is not None else -1.0,
                     nchw=nchw, accumulate=accumulate)
 
+    # ---- split-K for the 4^2 / 8^2 layers: a batch of 8 gives 1-4 tiles of 128 pixels and a 72-step serial K loop (9 taps x 512
+    # channels): the nine taps become nine concurrent work items per tile writing raw partial sums, summed in fixed order by
+    # n3d_splitk_epilogue (deterministic; an atomics-based variant was rejected for run-to-run differences).
+    def _use_splitk(self, res):
+        return self.splitk and self._N * res * res <= 512
+
+    def _splitk_conv(self, name, a, L, res, epi):
+        N, S = self._N, 9
+        part = self._f32(S, N, res, res, L.cout)
+        self._gemm(a.hi, a.lo, L.w_hi, L.w_lo, K.taps_conv3x3(), N, res, res, nprod=self.nprod, mode=1, out_f32=part, f32_cstride=L.cout,
+                    splits=S, split_stride=N * res * res * L.cout)
+        K.splitk_epilogue(part, **epi)
+        self.launches += 2
+
     def _modconv(self, name, a, res_in, outs, noise_mode, f32=None, rgb=None):
         """SynthesisLayer (networks_stylegan2.py:311-330); `a` already carries this layer's modulation."""
         L, N = self.mod[name], self._N
         self._cur_layer = name
         noise, nstride = self._noise(L, noise_mode)
         clamp = L.clamp if L.clamp is not None else -1.0
+        if L.up == 1 and self._use_splitk(res_in) and rgb is None:
+            self._splitk_conv(name, a, L, res_in, dict(dcoef=self._dcoef(L), bias=L.bias, noise=noise, noise_nstride=nstride, gain=SQRT2, slope=0.2,
+                                                        clamp=clamp, outs=outs, out_f32=f32, f32_cstride=L.cout if f32 is not None else 0))
+            return
         if L.up == 1:
             self._gemm(a.hi, a.lo, L.w_hi, L.w_lo, K.taps_conv3x3(), N, res_in, res_in, nprod=self.nprod, dcoef=self._dcoef(L), bias=L.bias,
                         noise=noise, noise_nstride=nstride, gain=SQRT2, slope=0.2, clamp=clamp, outs=outs, out_f32=f32,
@@ -308,6 +327,10 @@ class Engine:
         if stride2:
             self._gemm(a.hi, a.lo, L.w_hi, L.w_lo, K.taps_stride2(), N, res // 2, res // 2, a_img_mul=N, nprod=self.nprod, bias=L.bias, gain=gain,
                         slope=slope, outs=outs, out_f32=f32, f32_cstride=L.cout if f32 is not None else 0, f32_accumulate=accumulate)
+        elif L.k == 3 and self._use_splitk(res) and not accumulate:
+            self._splitk_conv(name, a, L, res, dict(dcoef=None, bias=L.bias, noise=None, gain=gain, slope=slope, clamp=-1.0, outs=outs, out_f32=f32,
+                                                    f32_cstride=L.cout if f32 is not None else 0))
+            return
         else:
             taps = K.taps_conv3x3() if L.k == 3 else K.taps_conv1x1()
             self._gemm(a.hi, a.lo, L.w_hi, L.w_lo, taps, N, res, res, nprod=self.nprod, bias=L.bias, gain=gain, slope=slope, outs=outs,

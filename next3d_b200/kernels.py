@@ -54,7 +54,7 @@ def make_split_out(hi=None, lo=None, style=None, cstride=0, coff=0):
 # ------------------------------------------------------------------------------------------------ kernels
 def conv_gemm(a_hi, a_lo, w_hi, w_lo, taps, N, MH, MW, *, a_img_mul=0, nprod=3, mode=0, dcoef=None, bias=None, noise=None,
               noise_nstride=0, gain=1.0, slope=1.0, clamp=-1.0, outs=(), out_f32=None, f32_cstride=0, f32_coff=0, f32_nchw=False,
-              f32_accumulate=False, oy_mul=1, oy_off=0, ox_mul=1, ox_off=0, OH=None, OW=None, rgb=None):
+              f32_accumulate=False, oy_mul=1, oy_off=0, ox_mul=1, ox_off=0, OH=None, OW=None, rgb=None, splits=1, split_stride=0):
     """a_*: bf16 [NI, AH, AW, Cin]; w_*: bf16 [T, Cout, Cin]; taps: list of (dy, dx, img_off, wtap)."""
     NI, AH, AW, Cin = a_hi.shape
     T, Cout, Cin_w = w_hi.shape
@@ -81,6 +81,7 @@ def conv_gemm(a_hi, a_lo, w_hi, w_lo, taps, N, MH, MW, *, a_img_mul=0, nprod=3, 
     if rgb is not None:                                  # dict(out, weight [c,Cout], style [N,Cout], bias [c], clamp, nchw, accumulate)
         p.rgb = _lib.FusedRgb(ptr(rgb['out']), ptr(rgb['weight']), ptr(rgb['style']), ptr(rgb['bias']), float(rgb.get('clamp', -1.0)),
                               rgb['weight'].shape[0], int(rgb.get('nchw', False)), int(rgb.get('accumulate', False)))
+    p.splits, p.split_stride = splits, split_stride
     check(lib.n3d_conv_gemm(C.byref(p), stream_ptr()), 'n3d_conv_gemm')
 
 
@@ -114,6 +115,16 @@ def fir_up_epilogue(raw, C_, dcoef, bias, noise, gain, slope, clamp, outs=(), ou
         arr[i] = o
     check(lib.n3d_fir_up_epilogue(ptr(raw), N, RH - 1, RW - 1, C_, ptr(dcoef), ptr(bias), ptr(noise), noise_nstride, gain, slope, clamp, arr,
                                   ptr(out_f32), f32_cstride, f32_coff, stream_ptr()), 'n3d_fir_up_epilogue')
+
+
+def splitk_epilogue(part, dcoef, bias, noise, gain, slope, clamp, outs=(), out_f32=None, f32_cstride=0, f32_coff=0, noise_nstride=0):
+    """part: fp32 [S, N, H, W, C] raw partial sums of a split-K conv_gemm (mode 1) -> summed, then the mode-0 epilogue."""
+    S, N, H, W, Cc = part.shape
+    arr = (_lib.SplitOut * 2)()
+    for i, o in enumerate(outs):
+        arr[i] = o
+    check(lib.n3d_splitk_epilogue(ptr(part), S, N * H * W * Cc, N, H, W, Cc, ptr(dcoef), ptr(bias), ptr(noise), noise_nstride, gain, slope, clamp, arr,
+                                  ptr(out_f32), f32_cstride, f32_coff, stream_ptr()), 'n3d_splitk_epilogue')
 
 
 def fir_down_split(x, hi, lo):

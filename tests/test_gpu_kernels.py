@@ -115,6 +115,41 @@ def test_conv1x1_torgb_nchw_accumulate(K):
     assert range_rel_err(out.cpu(), ref) < 3e-5
 
 
+@pytest.mark.parametrize('N,Cin,Cout,res,S', [(8, 512, 512, 4, 9), (8, 512, 512, 8, 9), (2, 32, 32, 16, 9), (3, 1024, 512, 8, 4), (1, 64, 96, 8, 3)])
+def test_conv_splitk(K, N, Cin, Cout, res, S):
+    """Split-K (deterministic two-pass): S K-slices write raw partial sums, n3d_splitk_epilogue sums them in fixed order and applies
+    the SynthesisLayer epilogue.  Same result as the one-pass kernel (up to fp32 summation order) and bit-reproducible."""
+    g = _g(23 + Cin + res)
+    x = torch.randn(N, Cin, res, res, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(Cin * 9)
+    d = torch.rand(N, Cout, generator=g) + 0.5
+    b = torch.randn(Cout, generator=g)
+    nz = torch.randn(res, res, generator=g) * 0.1
+    s1 = torch.randn(N, Cout, generator=g)
+    y = F.conv2d(x.double(), w.double(), padding=1).float() * d[:, :, None, None] + nz[None, None]
+    y = (F.leaky_relu(y + b[None, :, None, None], 0.2) * math.sqrt(2)).clamp(-2.0, 2.0)
+    a_hi, a_lo = _nhwc_split(K, x)
+    w_hi, w_lo = K.pack_conv_weight(w.to(DEV))
+    dd, bd, nzd, s1d = d.to(DEV), b.to(DEV), nz.to(DEV), s1.to(DEV)
+
+    def run():
+        part = torch.full((S, N, res, res, Cout), float('nan'), device=DEV)
+        K.conv_gemm(a_hi, a_lo, w_hi, w_lo, K.taps_conv3x3(), N, res, res, mode=1, out_f32=part, f32_cstride=Cout, splits=S,
+                    split_stride=N * res * res * Cout)
+        assert not torch.isnan(part).any()
+        o_hi = torch.zeros(N, res, res, Cout, device=DEV, dtype=torch.bfloat16)
+        o_lo = torch.zeros_like(o_hi)
+        f32 = torch.zeros(N, res, res, Cout, device=DEV)
+        K.splitk_epilogue(part, dd, bd, nzd, math.sqrt(2), 0.2, 2.0, outs=[K.make_split_out(o_hi, o_lo, s1d, Cout, 0)], out_f32=f32, f32_cstride=Cout)
+        return f32, o_hi, o_lo
+
+    f32, o_hi, o_lo = run()
+    assert range_rel_err(f32.permute(0, 3, 1, 2).cpu(), y) < 6e-5
+    assert range_rel_err(_join(o_hi, o_lo).permute(0, 3, 1, 2).cpu(), y * s1[:, :, None, None]) < 8e-5
+    f32b, _, _ = run()
+    assert torch.equal(f32, f32b)
+
+
 @pytest.mark.parametrize('N,Cin,Cout,res,nchw,with_out', [(2, 64, 128, 32, True, True), (1, 128, 256, 16, False, True), (2, 32, 128, 32, True, False),
                                                          (2, 32, 128, 280, True, False)])     # last: pair-tile mode
 def test_conv_fused_torgb(K, N, Cin, Cout, res, nchw, with_out):
