@@ -274,7 +274,7 @@ class Engine:
     # channels): the nine taps become nine concurrent work items per tile writing raw partial sums, summed in fixed order by
     # n3d_splitk_epilogue (deterministic; an atomics-based variant was rejected for run-to-run differences).
     def _use_splitk(self, res):
-        return self.splitk and self._N * res * res <= 512
+        return self.splitk and res <= 8          # by resolution only: the summation order of a sample must not depend on the batch size
 
     def _splitk_conv(self, name, a, L, res, epi):
         N, S = self._N, 9
