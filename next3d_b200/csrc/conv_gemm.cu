@@ -28,6 +28,7 @@ constexpr int kBlockM = 128;
 constexpr int kThreads = 384;                 // warps 0-3: producer / MMA / TMEM alloc / spare; 4-7 and 8-11: two epilogue groups
 constexpr int kMaxBlockN = 256;
 constexpr int kMinTiles = 64;                 // see the block_n choice in launch_conv
+constexpr int kMinTilesSplit = 128;           // same for split-K launches
 constexpr int kStageArrays = 8;               // dcoef | bias | style0 | style1 | up to 4 modulated ToRGB weight rows
 
 struct KParams {
@@ -495,7 +496,12 @@ int launch_conv(const N3DConvGemm* p, int nsub, const SubSpec* specs, void* stre
             bn = cands[i];
             break;
         }
-        while (bn > 32 && tiles_m * splits * n3d_div_up(p->Cout, bn) < kMinTiles) bn = (bn == 96) ? 32 : bn / 2;
+        int min_tiles = kMinTiles;
+        if (splits > 1) {                                   // split launches: short K loops, so spread over (nearly) all SMs
+            min_tiles = kMinTilesSplit;
+            if (const char* e = getenv("N3D_SPLITK_MINTILES")) min_tiles = atoi(e);      // A/B diagnostics (tools/bench_splitk.py)
+        }
+        while (bn > 32 && tiles_m * splits * n3d_div_up(p->Cout, bn) < min_tiles) bn = (bn == 96) ? 32 : bn / 2;
         if (p->rgb.out) {                                   // fused ToRGB needs every output channel of a pixel in one tile
             N3D_CHECK_ARG(cout16 <= 256 && cout16 % 16 == 0, "n3d_conv_gemm: fused ToRGB needs Cout <= 256");
             N3D_CHECK_ARG(p->rgb.channels >= 1 && p->rgb.channels <= 4 && p->rgb.weight && p->rgb.style && p->rgb.bias, "n3d_conv_gemm: bad fused ToRGB descriptor");

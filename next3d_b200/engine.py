@@ -86,6 +86,7 @@ class Engine:
         self._side = None                       # side streams of the concurrent branches (compute_planes)
         self.concurrent = os.environ.get('N3D_CONCURRENT', '1') != '0'
         self.splitk = os.environ.get('N3D_SPLITK', '1') != '0'
+        self.splitk_maxres = int(os.environ.get('N3D_SPLITK_MAXRES', '16'))
 
     # ------------------------------------------------------------------------------------------ packing (one-time)
     def _add_mod(self, sd, name, cin, cout, k, up, widx, is_rgb=False, clamp=None, noise=True):
@@ -274,7 +275,7 @@ class Engine:
     # channels): the nine taps become nine concurrent work items per tile writing raw partial sums, summed in fixed order by
     # n3d_splitk_epilogue (deterministic; an atomics-based variant was rejected for run-to-run differences).
     def _use_splitk(self, res):
-        return self.splitk and res <= 8          # by resolution only: the summation order of a sample must not depend on the batch size
+        return self.splitk and res <= self.splitk_maxres   # by resolution only: the summation order of a sample must not depend on the batch size
 
     def _splitk_conv(self, name, a, L, res, epi):
         N, S = self._N, 9
