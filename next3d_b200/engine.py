@@ -635,7 +635,7 @@ class Engine:
             return self._synthesis_graphed(ws, c, v, noise_mode, neural_rendering_resolution, seed)
 
     def _synthesis_graphed(self, ws, c, v, noise_mode='const', neural_rendering_resolution=None, seed=0):
-        """Same as synthesis() (in-kernel sampler RNG) but the 185 launches of one forward are captured once per
+        """Same as synthesis() (in-kernel sampler RNG) but the ~200 launches of one forward are captured once per
         (batch, resolution, noise_mode) into a CUDA graph and replayed: removes the host-side launch latency that otherwise
         leaves the GPU idle between kernels.  Inputs are copied into static buffers; the returned tensors are the graph's
         static outputs and are overwritten by the next call with the same key."""

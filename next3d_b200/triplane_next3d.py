@@ -72,7 +72,7 @@ class TriPlaneGenerator(torch.nn.Module):
                 _attach(self, name, torch.zeros(shape), kind in _PARAM_KINDS)
         self._engine = None
         self._engine_key = None
-        self.use_cuda_graph = False      # opt-in: replay one captured CUDA graph per (batch, resolution) instead of 185 launches
+        self.use_cuda_graph = False      # opt-in: replay one captured CUDA graph per (batch, resolution) instead of ~200 launches
 
     @staticmethod
     def _load_uv_face_mask(path='data/ffhq/uv_face_eye_mask.png'):
