@@ -125,7 +125,7 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([time.perf_counter()] + [x.strip() for x in line.split(',')])
 
-    def stop(self, window=None):
+    def stop(self, window=None, scope='timed region + e2e loop (same load)'):
         """Median SM clock / throttle reasons of the samples that arrived inside `window` = (t0, t1) perf_counter times of the
         timed region; if nvidia-smi delivered none in there (the region is a few hundred ms), of all samples taken under the same
         load (timed region + end-to-end loop), and says which."""
@@ -136,7 +136,7 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        rows, scope = self.rows, 'timed region + e2e loop (same load)'
+        rows = self.rows
         if window is not None:
             inside = [r for r in self.rows if window[0] <= r[0] <= window[1]]
             if inside:
@@ -381,20 +381,28 @@ def run_ours(args):
         z, c_cond, _, v = weights.demo_inputs(cfg, 1, seed=0)
         with torch.no_grad():
             ws = G.mapping(z.to(dev), c_cond.to(dev), truncation_psi=0.7, truncation_cutoff=14)
+            sampler = ClockSampler(local) if rank == 0 else None
+            if sampler:
+                sampler.start()
             ms, roof = _time_c5(G, ws, v.to(dev), args.steps, args.warmup)
+            clocks = sampler.stop(scope='warm-up + timed region (same load)') if sampler else None
         ms = 1e3 * D.max_over_ranks(ms / 1e3, dev)
         if rank == 0:
             _emit({'metric': spec['metric'], 'value': world * 1e3 / ms, 'unit': 'grids/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
                    'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16x3 decoder (fp32 accumulate), f32 elsewhere',
                    'data': 'synthetic', 'config': {'workload': spec['workload'] + 'one grid per GPU (replicas only: a single grid does not shard in the script)'},
-                   'roofline': roof, 'gpu_launches': args.steps})
+                   'roofline': roof, 'clocks': clocks, 'gpu_launches': args.steps})
         if world > 1:
             dist.destroy_process_group()
         return
 
     if name == 'c4':
         G.use_cuda_graph = not args.no_graph
+        sampler = ClockSampler(local) if rank == 0 else None
+        if sampler:
+            sampler.start()
         dt, F, ok = _time_c4(G, dev, rank, world, max(1, min(args.steps, 3)), args.warmup)
+        clocks = sampler.stop(scope='warm-up + timed region (same load)') if sampler else None
         if rank == 0:
             _emit({'metric': spec['metric'], 'value': F / dt, 'unit': UNIT, 'n_gpus': world, 'steps': max(1, min(args.steps, 3)), 'warmup': args.warmup,
                    'ms_per_step': 1e3 * dt, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
@@ -402,7 +410,7 @@ def run_ours(args):
                    'config': {'workload': spec['workload'] + f'batches of {spec["batch"]} frames per GPU', 'frames': F,
                               'parallelism': f'frames sharded x{world}, uint8 frames gathered to rank 0 on a side stream, read back to pinned host memory',
                               'step': 'one step = the whole clip'},
-                   'frames_ok': ok,
+                   'frames_ok': ok, 'clocks': clocks,
                    'e2e': {'value': F / dt, 'unit': UNIT, 'h2d_bytes_per_step': int(F * (28 * 512 + 25) * 4),
                            'd2h_bytes_per_step': int(F * 512 * 512 * 3), 'ms_per_step': 1e3 * dt,
                            'note': 'this configuration IS end to end: host schedule -> H2D per batch -> synthesis -> uint8 -> gather -> D2H'},
