@@ -534,7 +534,8 @@ def run_ours(args):
                     'unit': 'TFLOP/s', 'frac': ach / pk['tf'], 'traffic': tr_g, 'traffic_unit': 'DRAM bytes per launch (mean)', 'traffic_source': tr_src,
                     'peak_source': pk['src'], 'launches_per_step': n_g,
                     'ms_per_step': ms_g, 'share_of_step': ms_g / step_ms,
-                    'note': 'algorithmic FLOPs (one product per MAC: %.1f GFLOP/img); the bf16x3 scheme executes 3x that on the tensor pipe' % (fl_g / B / 1e9)}
+                    'note': 'algorithmic FLOPs (one product per MAC: %.1f GFLOP/img); the bf16x3 scheme executes 3x that on the tensor pipe; '
+                            'launches and time include the fixed-order reduction passes of the split-K 4^2-16^2 layers' % (fl_g / B / 1e9)}
             n_r, ms_r, _ = summ['render_rays']
             roof_r = _renderer_roofline(name, cfg, B, ms_r, step_ms, pk)
             tr_r, tr_rsrc = _traffic('render_fused_kernel') if (B == 8 and name == 'c2') else (None, None)

@@ -282,7 +282,9 @@ class Engine:
         part = self._f32(S, N, res, res, L.cout)
         self._gemm(a.hi, a.lo, L.w_hi, L.w_lo, K.taps_conv3x3(), N, res, res, nprod=self.nprod, mode=1, out_f32=part, f32_cstride=L.cout,
                     splits=S, split_stride=N * res * res * L.cout)
+        ev = self._prof_begin()                  # the reduction pass is part of this convolution: counted as conv time (0 extra FLOPs)
         K.splitk_epilogue(part, **epi)
+        self._prof_end(ev, 'conv_gemm', 0.0, (name, a.hi.shape[-1], L.cout, res, res, 0))
         self.launches += 2
 
     def _modconv(self, name, a, res_in, outs, noise_mode, f32=None, rgb=None):

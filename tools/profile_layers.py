@@ -20,7 +20,7 @@ G.synthesis(ws, c.cuda(), v.cuda(), noise_mode='const', seed=1)
 torch.cuda.synchronize()
 rows = [(info, e0.elapsed_time(e1) * 1e3, fl) for kind, e0, e1, fl, info in eng.prof if kind == 'conv_gemm']
 tot = sum(r[1] for r in rows)
-print(f'batch {B}: {len(rows)} conv_gemm launches, {tot/1e3:.2f} ms, {sum(r[2] for r in rows)/tot/1e6:.1f} TFLOP/s algorithmic (x3 executed)')
+print(f'batch {B}: {len(rows)} conv_gemm launches (incl. the split-K reduction passes, listed with the layer), {tot/1e3:.2f} ms, {sum(r[2] for r in rows)/tot/1e6:.1f} TFLOP/s algorithmic (x3 executed)')
 print(f'{"layer":58s} {"Cin":>5s} {"Cout":>5s} {"M-space":>9s} {"taps":>4s} {"us":>8s} {"TF/s":>7s} {"%":>5s}')
 agg = {}
 for (name, cin, cout, mh, mw, taps), us, fl in rows:
