@@ -1,8 +1,11 @@
 // Memory-bound glue kernels of the generator engine (everything between two tensor-core convolutions that could not be
 // folded into a GEMM epilogue).  All tensors NHWC; 128-bit accesses along the channel dimension; grids sized in
 // multiples of the SM count.
+#include <cstdlib>
 #include "common.cuh"
 #include "../../include/next3d_b200.h"
+#include <cuda.h>
+#include "tc_ptx.cuh"
 
 namespace {
 constexpr int kSMs = 148;
@@ -250,6 +253,115 @@ __global__ void __launch_bounds__(256) fir_up_epilogue_kernel(const float* __res
     }
 }
 
+// ---------------------------------------------------------------------------------------------- streamed FIR-up epilogue
+// Same arithmetic as fir_up_epilogue_kernel<2> (bit-identical results), different data movement.  The register-tiled kernel above is
+// bound by load latency at 16 warps/SM (DRAM 42-62 % of peak, profiles/r02_ncu_glue.txt): every strip step waits for its own ten
+// 16-byte loads.  Here a CTA owns a (TR output rows) x (TC output columns) x (all C channels) tile of one image and a producer
+// thread streams the raw rows it needs -- each a CONTIGUOUS (TC + 3) * C * 4-byte segment of the NHWC tensor -- through a ring of
+// shared-memory stages with 1-D bulk copies (TMA engine, mbarrier full / empty pairs); the eight consumer warps read the five
+// columns of their 2-column output block from shared memory.  Loads are in flight NR rows ahead of the arithmetic and cost no
+// registers.  thread = (column pair, 4-channel group): (TC / 2) * (C / 4) == 256.
+constexpr int kFsConsumers = 256, kFsThreads = kFsConsumers + 32;
+
+__global__ void __launch_bounds__(kFsThreads, 2) fir_up_stream_kernel(const float* __restrict__ raw, int N, int H2, int W2, int C, int TC, int TR, int NR,
+                                                                       EpiParams E) {
+    using namespace n3d_tc;
+    extern __shared__ __align__(128) uint8_t fs_smem[];
+    const int RH = H2 + 1, RW = W2 + 1, c4n = C >> 2;
+    const int row_f4 = (TC + 3) * c4n;                          // float4 per stage (one raw row segment)
+    const uint32_t row_bytes = (uint32_t)row_f4 * 16u;
+    const uint32_t ring = smem_u32(fs_smem), bars = ring + (uint32_t)NR * row_bytes;
+    auto full_bar = [&](int s) { return bars + 8u * (uint32_t)s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (uint32_t)(NR + s); };
+    const int tiles_x = W2 / TC, tiles_y = H2 / TR;
+    const int bx = blockIdx.x % tiles_x, by = (blockIdx.x / tiles_x) % tiles_y, n = blockIdx.x / (tiles_x * tiles_y);
+    const int X0 = bx * TC, Y0 = by * TR;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NR; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), kFsConsumers / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == kFsConsumers / 32) {
+        // ===================================================== producer: raw rows Y0-1 .. Y0+TR+1, columns X0-1 .. X0+TC+1 (clipped)
+        if (lane == 0) {
+            const int col_lo = max(X0 - 1, 0), col_hi = min(X0 + TC + 1, RW - 1);
+            const uint32_t bytes = (uint32_t)(col_hi - col_lo + 1) * (uint32_t)C * 4u;
+            const uint32_t dst_off = (uint32_t)(col_lo - (X0 - 1)) * (uint32_t)C * 4u;
+            const float* src = raw + ((int64_t)n * RH * RW + col_lo) * C;
+            int s = 0; uint32_t ph = 0;
+            for (int ry = Y0 - 1; ry <= Y0 + TR + 1; ++ry) {
+                if (ry < 0 || ry >= RH) continue;               // zero padding: the consumers skip the same rows
+                mbar_wait_short(empty_bar(s), ph ^ 1u);
+                mbar_expect_tx(full_bar(s), bytes);
+                bulk_load_1d(ring + (uint32_t)s * row_bytes + dst_off, src + (int64_t)ry * RW * C, bytes, full_bar(s));
+                if (++s == NR) { s = 0; ph ^= 1u; }
+            }
+        }
+        return;
+    }
+
+    // ========================================================= consumers
+    const int c4 = threadIdx.x % c4n, j = threadIdx.x / c4n;
+    const int x0 = X0 + 2 * j, c0 = c4 * 4;
+    const bool vl = x0 > 0, vr = x0 + 3 < RW;                   // raw columns x0-1 .. x0+3
+    const float4* base = reinterpret_cast<const float4*>(fs_smem) + (2 * j) * c4n + c4;
+    const float g[4] = {0.25f, 0.75f, 0.75f, 0.25f};
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    int s = 0; uint32_t ph = 0;
+    auto hrow = [&](int ry, float4 (&h)[2]) {
+        h[0] = z; h[1] = z;
+        if (ry < 0 || ry >= RH) return;
+        mbar_wait_short(full_bar(s), ph);
+        const float4* p = base + s * row_f4;
+        float4 v[5];
+        v[0] = vl ? p[0] : z;
+#pragma unroll
+        for (int q = 1; q < 4; ++q) v[q] = p[q * c4n];
+        v[4] = vr ? p[4 * c4n] : z;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            h[b] = f4_scale(g[0], v[b]);
+#pragma unroll
+            for (int fx = 1; fx < 4; ++fx) h[b] = f4_fma(g[fx], v[b + fx], h[b]);
+        }
+        __syncwarp();                                           // every lane has consumed its values: the stage may be refilled
+        if (lane == 0) mbar_arrive(empty_bar(s));
+        if (++s == NR) { s = 0; ph ^= 1u; }
+    };
+    const EpiVec V = epi_load(E, n, C, c0);
+    const float* nzp = E.noise ? E.noise + (int64_t)n * E.noise_nstride + x0 : nullptr;
+    float4 h[5][2];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) hrow(Y0 - 1 + r, h[r]);
+    EpiCursor P = epi_cursor(E, ((int64_t)n * H2 + Y0) * W2 + x0, c0);
+    const int64_t adv_f32 = 2 * (int64_t)W2 * E.f32_cstride, adv0 = 2 * (int64_t)W2 * E.out[0].cstride, adv1 = 2 * (int64_t)W2 * E.out[1].cstride;
+    for (int y0 = Y0; y0 < Y0 + TR; y0 += 2, P.f32 += adv_f32, P.sp[0] += adv0, P.sp[1] += adv1) {
+        hrow(y0 + 2, h[3]);
+        hrow(y0 + 3, h[4]);
+        float nz[2][2];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) nz[a][b] = nzp ? E.gain * __ldg(nzp + (int64_t)(y0 + a) * W2 + b) : 0.f;
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                float4 acc = f4_scale(g[0], h[a][b]);
+#pragma unroll
+                for (int r = 1; r < 4; ++r) acc = f4_fma(g[r], h[a + r][b], acc);
+                epi_store(E, V, P, acc, nz[a][b], a * W2 + b);
+            }
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) h[r][b] = h[r + 2][b];
+    }
+}
+
 // Second pass of a split-K convolution: sum the S raw partial tensors in a fixed order, then the usual epilogue.
 // thread = (pixel, 4-channel group).
 __global__ void __launch_bounds__(256) splitk_epilogue_kernel(const float* __restrict__ part, int S, int64_t stride, int N, int H, int W, int C, EpiParams E) {
@@ -472,6 +584,30 @@ extern "C" int n3d_fir_up_epilogue(const float* raw, int N, int H2, int W2, int 
         N3D_CHECK_ARG(!E.out[k].hi || ((E.out[k].cstride % 4 == 0) && (E.out[k].coff % 4 == 0)), "n3d_fir_up_epilogue: unaligned split output");
     N3D_CHECK_ARG(!out_f32 || (f32_cstride % 4 == 0 && f32_coff % 4 == 0), "n3d_fir_up_epilogue: unaligned fp32 output");
     N3D_CHECK_ARG(H2 % 2 == 0 && W2 % 2 == 0, "n3d_fir_up_epilogue: output size must be even");
+    {   // streamed variant (fir_up_stream_kernel) for the large layers: (TC / 2) * (C / 4) == 256 consumer threads, >= one CTA per SM
+        const char* e = getenv("N3D_FIR_STREAM");               // N3D_FIR_STREAM=0: the register-tiled kernel (A/B diagnostics, tests)
+        const int stream_mode = e ? atoi(e) : 1;
+        const int TC = (C >= 64 && C <= 512 && (2048 % C) == 0) ? 2048 / C : 0;
+        const int TR = H2 >= 256 ? 64 : 32;
+        if (stream_mode && TC >= 4 && W2 % TC == 0 && H2 % TR == 0 && ((uintptr_t)raw & 15) == 0 &&
+            (int64_t)N * (W2 / TC) * (H2 / TR) >= 148) {
+            const int row_bytes = (TC + 3) * C * 4;
+            const int NR = min(8, (100 * 1024) / row_bytes);
+            const int smem = NR * row_bytes + 16 * NR;
+            N3DDeviceState* D = n3d_device_state();
+            if (!D) return N3D_ERR_CUDA;
+            if (!(D->configured & N3D_CFG_FIR_STREAM)) {
+                if (cudaFuncSetAttribute(fir_up_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024) != cudaSuccess) {
+                    n3d_set_error("n3d_fir_up_epilogue: cannot raise dynamic shared memory to 112 KiB");
+                    return N3D_ERR_CUDA;
+                }
+                D->configured |= N3D_CFG_FIR_STREAM;
+            }
+            fir_up_stream_kernel<<<N * (W2 / TC) * (H2 / TR), kFsThreads, smem, (cudaStream_t)stream>>>(raw, N, H2, W2, C, TC, TR, NR, E);
+            N3D_CHECK_LAUNCH("n3d_fir_up_epilogue");
+            return N3D_OK;
+        }
+    }
     const int S = fir_strip_rows((int64_t)N * (W2 / 2) * (C / 4), H2 / 2);
     const int64_t total = (int64_t)N * n3d_div_up(H2 / 2, S) * (W2 / 2) * (C / 4);
     // 2 output columns per thread: measured best on B200 (1 column: +23 % time despite 1.5x the occupancy, 4 columns: +15 %)

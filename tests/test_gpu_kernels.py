@@ -212,6 +212,42 @@ def test_upconv_modulated(K, N, Cin, Cout, res):
     assert range_rel_err(out.permute(0, 3, 1, 2).cpu(), ref) < 3e-5
 
 
+@pytest.mark.parametrize('N,C,H2', [(3, 128, 256), (3, 256, 128), (5, 512, 64), (5, 64, 256), (1, 128, 512)])
+def test_fir_up_streamed_kernel_is_bit_identical(K, N, C, H2, monkeypatch):
+    """The large layers take the streamed variant (bulk copies of raw rows through a shared-memory ring); it must reproduce the
+    register-tiled kernel bit for bit -- fp32 copy, both modulated split-bf16 outputs (one into a concat buffer at a channel offset),
+    noise, clamp -- and both must match an fp64 evaluation of upfirdn2d (upfirdn2d.py:120-164, pad 1/1, gain 4) + bias_act."""
+    g = _g(31 + C + H2)
+    raw = torch.randn(N, H2 + 1, H2 + 1, C, generator=g).to(DEV)
+    d, b = (torch.rand(N, C, generator=g) + 0.5).to(DEV), torch.randn(C, generator=g).to(DEV)
+    nz = (torch.randn(H2, H2, generator=g) * 0.1).to(DEV)
+    s0, s1 = torch.randn(N, C, generator=g).to(DEV), torch.randn(N, C, generator=g).to(DEV)
+
+    def run(mode):
+        monkeypatch.setenv('N3D_FIR_STREAM', mode)
+        f32 = torch.zeros(N, H2, H2, C, device=DEV)
+        o0 = [torch.zeros(N, H2, H2, C, device=DEV, dtype=torch.bfloat16) for _ in range(2)]
+        o1 = [torch.zeros(N, H2, H2, 2 * C, device=DEV, dtype=torch.bfloat16) for _ in range(2)]      # concat buffer, second half
+        outs = [K.make_split_out(o0[0], o0[1], s0, C, 0), K.make_split_out(o1[0], o1[1], s1, 2 * C, C)]
+        K.fir_up_epilogue(raw, C, d, b, nz, math.sqrt(2), 0.2, 1.5, outs=outs, out_f32=f32, f32_cstride=C)
+        torch.cuda.synchronize()
+        return [f32] + o0 + o1
+
+    a, bb = run('1'), run('0')
+    for x, y in zip(a, bb):
+        assert torch.equal(x, y)
+    f1 = torch.tensor([1., 3., 3., 1.], dtype=torch.float64, device=DEV) / 4
+    x = raw.double().permute(0, 3, 1, 2)
+    x = F.pad(x, (1, 1, 1, 1))
+    y = F.conv2d(x.reshape(N * C, 1, H2 + 3, H2 + 3), torch.outer(f1, f1)[None, None]).reshape(N, C, H2, H2)
+    y = y * d.double()[:, :, None, None] + nz.double()[None, None] + b.double()[None, :, None, None]
+    y = (F.leaky_relu(y, 0.2) * math.sqrt(2)).clamp(-1.5, 1.5)
+    assert range_rel_err(a[0].permute(0, 3, 1, 2).cpu(), y.cpu()) < 1e-6
+    assert range_rel_err(_join(a[1], a[2]).permute(0, 3, 1, 2).cpu(), (y * s0.double()[:, :, None, None]).cpu()) < 2e-5
+    assert range_rel_err(_join(a[3], a[4])[..., C:].permute(0, 3, 1, 2).cpu(), (y * s1.double()[:, :, None, None]).cpu()) < 2e-5
+    assert float(a[3][..., :C].abs().max()) == 0.0              # the other half of the concat buffer is untouched
+
+
 @pytest.mark.parametrize('N,Cin,Cout,res', [(2, 64, 64, 16), (1, 128, 256, 64), (1, 32, 32, 8)])
 def test_downconv(K, N, Cin, Cout, res):
     from oracle import ops as oo

@@ -46,9 +46,14 @@ def main(tag):
         nz = torch.randn(2 * res, 2 * res, device=DEV)
         st = torch.randn(N, cout, device=DEV)
         outs = [K.make_split_out(o_hi, o_lo, st, cout, 0)]
-        us = timeit(lambda: K.fir_up_epilogue(raw, cout, d, b, nz, 2 ** 0.5, 0.2, 256.0, outs=outs))
         gb = raw.numel() * 4 + o_hi.numel() * 4
-        print(f'fir_up  C={cout:4d} out {2 * res:3d}^2      {us:8.1f} us  {gb / us * 1e-3:6.0f} GB/s')
+        for mode in ('0', '1'):                      # 0: register-tiled kernel, 1: streamed kernel where eligible
+            os.environ['N3D_FIR_STREAM'] = mode
+            us = timeit(lambda: K.fir_up_epilogue(raw, cout, d, b, nz, 2 ** 0.5, 0.2, 256.0, outs=outs))
+            print(f'fir_up  C={cout:4d} out {2 * res:3d}^2 stream={mode} {us:8.1f} us  {gb / us * 1e-3:6.0f} GB/s')
+        os.environ.pop('N3D_FIR_STREAM')
+    if os.environ.get('FIR_ONLY'):
+        return
     for cin, cout, res in [(128, 128, 512), (128, 128, 256), (256, 256, 128), (512, 512, 64), (512, 512, 32), (512, 512, 16), (512, 512, 8), (512, 512, 4),
                            (1024, 512, 32), (1024, 512, 16), (1024, 512, 8)]:
         x = torch.randn(N, res, res, cin, device=DEV, generator=g)
