@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(256) fir_up_epilogue_kernel(const float* __res
 #pragma unroll
             for (int a = 0; a < 2; ++a)
 #pragma unroll
-                for (int b = 0; b < NC; ++b) nz[a][b] = nzp ? E.gain * __ldg(nzp + (int64_t)(y0 + a) * W2 + b) : 0.f;
+                for (int b = 0; b < NC; ++b) nz[a][b] = nzp ? __fmul_rn(E.gain, __ldg(nzp + (int64_t)(y0 + a) * W2 + b)) : 0.f;   // explicit: no FMA contraction into the bias add
 #pragma unroll
             for (int a = 0; a < 2; ++a)
 #pragma unroll
@@ -338,14 +338,25 @@ __global__ void __launch_bounds__(kFsThreads, 2) fir_up_stream_kernel(const floa
     for (int r = 0; r < 3; ++r) hrow(Y0 - 1 + r, h[r]);
     EpiCursor P = epi_cursor(E, ((int64_t)n * H2 + Y0) * W2 + x0, c0);
     const int64_t adv_f32 = 2 * (int64_t)W2 * E.f32_cstride, adv0 = 2 * (int64_t)W2 * E.out[0].cstride, adv1 = 2 * (int64_t)W2 * E.out[1].cstride;
+    // the noise of a 2x2 block is fetched one strip step ahead: its global-load latency was 26 % of all stall samples when it sat
+    // between the FIR and the stores (ncu source page of the first version)
+    float nzn[2][2];
+    auto load_noise = [&](int y0) {
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) nzn[a][b] = nzp ? __ldg(nzp + (int64_t)(y0 + a) * W2 + b) : 0.f;
+    };
+    load_noise(Y0);
     for (int y0 = Y0; y0 < Y0 + TR; y0 += 2, P.f32 += adv_f32, P.sp[0] += adv0, P.sp[1] += adv1) {
-        hrow(y0 + 2, h[3]);
-        hrow(y0 + 3, h[4]);
         float nz[2][2];
 #pragma unroll
         for (int a = 0; a < 2; ++a)
 #pragma unroll
-            for (int b = 0; b < 2; ++b) nz[a][b] = nzp ? E.gain * __ldg(nzp + (int64_t)(y0 + a) * W2 + b) : 0.f;
+            for (int b = 0; b < 2; ++b) nz[a][b] = __fmul_rn(E.gain, nzn[a][b]);     // same rounding as the register-tiled kernel
+        if (y0 + 2 < Y0 + TR) load_noise(y0 + 2);
+        hrow(y0 + 2, h[3]);
+        hrow(y0 + 3, h[4]);
 #pragma unroll
         for (int a = 0; a < 2; ++a)
 #pragma unroll
@@ -379,7 +390,7 @@ __global__ void __launch_bounds__(256) splitk_epilogue_kernel(const float* __res
         }
         const EpiVec V = epi_load(E, n, C, c4 * 4);
         const EpiCursor P = epi_cursor(E, pix, c4 * 4);
-        const float nzg = E.noise ? E.gain * __ldg(E.noise + (int64_t)n * E.noise_nstride + yx) : 0.f;
+        const float nzg = E.noise ? __fmul_rn(E.gain, __ldg(E.noise + (int64_t)n * E.noise_nstride + yx)) : 0.f;
         epi_store(E, V, P, acc, nzg, 0);
     }
 }
@@ -588,11 +599,25 @@ extern "C" int n3d_fir_up_epilogue(const float* raw, int N, int H2, int W2, int 
         const char* e = getenv("N3D_FIR_STREAM");               // N3D_FIR_STREAM=0: the register-tiled kernel (A/B diagnostics, tests)
         const int stream_mode = e ? atoi(e) : 1;
         const int TC = (C >= 64 && C <= 512 && (2048 % C) == 0) ? 2048 / C : 0;
-        const int TR = H2 >= 256 ? 64 : 32;
-        if (stream_mode && TC >= 4 && W2 % TC == 0 && H2 % TR == 0 && ((uintptr_t)raw & 15) == 0 &&
+        // rows per tile: the candidate with the best (fill of the last wave of 2 CTAs per SM) x (1 - vertical halo); measured sweep in
+        // DESIGN.md section 3.3.  The tiling does not change the arithmetic (results are bit-identical for every TR).
+        int TR = 0;
+        if (TC >= 4 && W2 % TC == 0) {
+            double best = 0.0;
+            for (int tr = 32; tr <= 128; tr *= 2) {
+                if (H2 % tr) continue;
+                const int64_t ctas = (int64_t)N * (W2 / TC) * (H2 / tr);
+                if (ctas < 148) continue;
+                const double eff = (double)ctas / (double)(n3d_div_up(ctas, 296) * 296) * tr / (tr + 3);
+                if (eff > best) { best = eff; TR = tr; }
+            }
+        }
+        if (const char* t = getenv("N3D_FIR_TR")) { TR = atoi(t); if (TR > H2) TR = H2; }      // tuning sweep only
+        if (stream_mode && TR > 0 && TC >= 4 && W2 % TC == 0 && H2 % TR == 0 && ((uintptr_t)raw & 15) == 0 &&
             (int64_t)N * (W2 / TC) * (H2 / TR) >= 148) {
             const int row_bytes = (TC + 3) * C * 4;
-            const int NR = min(8, (100 * 1024) / row_bytes);
+            int NR = min(4, (100 * 1024) / row_bytes);         // deeper rings measured 1-3 % slower (sweep 4 / 6 / 8 / 10)
+            if (const char* t = getenv("N3D_FIR_NR")) NR = max(3, min(atoi(t), (110 * 1024) / row_bytes));
             const int smem = NR * row_bytes + 16 * NR;
             N3DDeviceState* D = n3d_device_state();
             if (!D) return N3D_ERR_CUDA;
