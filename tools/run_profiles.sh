@@ -17,9 +17,9 @@ N3D_BENCH_GRID=0 ncu --set full --clock-control none --import-source on -k regex
 N3D_BENCH_GRID=0 ncu --set full --clock-control none --import-source on -k regex:render_fused -s 3 -c 1 -f -o gpurun_out/prof_render_c3_$R python tools/bench_render.py c3 > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:points_fused -s 2 -c 1 -f -o gpurun_out/prof_points_$R python tools/bench_render.py c2 > /dev/null 2>&1
 fi
-ncu --set full --clock-control none -k "regex:^(rasterize|raster_setup|uv_sample|fill_mouth|resize_aa|transform|blend|mouth_box|fir_up|fir_down|splitk_|upsample2d|downsample2d|styles|demod|modulate_split|mapping|depth_clamp)" \
-    -s 130 -c 50 -f -o gpurun_out/prof_glue_$R python bench.py --no-graph --steps 1 --warmup 3 --no-cpu-baseline --no-other-configs > /dev/null 2>&1
-python tools/summarize_ncu.py gpurun_out/prof_glue_$R.ncu-rep > gpurun_out/ncu_glue_$R.txt 2>&1; rm -f gpurun_out/prof_glue_$R.ncu-rep      # gpurun_out/ must stay below 64 MiB
+# every non-GEMM, non-renderer kernel of ONE forward (98 launches after 3 warm-up forwards), summarised as the longest launch per kernel
+ncu --set full --clock-control none -k "regex:^(styles|demod|modulate_split|fir_|splitk_|upsample2d|downsample2d|transform|raster|uv_sample|fill_mouth|mouth_box|resize_aa|blend|depth_clamp)" -s 294 -c 98 -f -o gpurun_out/prof_glue_$R python bench.py --no-graph --steps 1 --warmup 3 --no-cpu-baseline --no-other-configs > /dev/null 2>&1
+python tools/summarize_ncu.py gpurun_out/prof_glue_$R.ncu-rep longest > gpurun_out/ncu_glue_$R.txt 2>&1; rm -f gpurun_out/prof_glue_$R.ncu-rep      # gpurun_out/ must stay below 64 MiB
 ncu --set full --clock-control none -k "regex:(upfirdn2d_kernel|bias_act_kernel|flrelu)" -c 8 -f -o gpurun_out/prof_ops_$R python -m pytest tests/test_gpu_ops_api.py -q -m gpu > /dev/null 2>&1
 python tools/summarize_ncu.py gpurun_out/prof_ops_$R.ncu-rep > gpurun_out/ncu_ops_$R.txt 2>&1; rm -f gpurun_out/prof_ops_$R.ncu-rep
 if [ "$3" != "noreps" ]; then

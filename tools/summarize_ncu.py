@@ -1,5 +1,5 @@
 """Summarise an .ncu-rep (ncu --set full) into the handful of metrics DESIGN.md / bench.py quote.
-Usage: python tools/summarize_ncu.py gpurun_out/prof.ncu-rep > profiles/rNN_xxx.txt   (runs where ncu is installed, no GPU needed)"""
+Usage: python tools/summarize_ncu.py gpurun_out/prof.ncu-rep [longest] > profiles/rNN_xxx.txt   (runs where ncu is installed, no GPU needed)"""
 import csv
 import io
 import subprocess
@@ -16,11 +16,21 @@ KEYS = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'la
         'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio']
 
 
-def main(path):
+def main(path, longest_only=False):
     raw = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     h, units, data = rows[0], rows[1], rows[2:]
     name_i = h.index('Kernel Name')
+    if longest_only:                 # one entry per kernel name: its longest launch (+ how many launches the capture held)
+        ti = h.index('gpu__time_duration.sum')
+        best, count = {}, {}
+        for r in data:
+            k = r[name_i].split('(')[0]
+            count[k] = count.get(k, 0) + 1
+            if k not in best or float(r[ti].replace(',', '')) > float(best[k][ti].replace(',', '')):
+                best[k] = r
+        data = list(best.values())
+        print('# longest launch of every kernel in the capture; launches captured:', ', '.join(f'{k.split("::")[-1]} x{n}' for k, n in count.items()))
     for li, r in enumerate(data):
         print(f'=== launch {li}: {r[name_i][:90]}')
         for k in KEYS:
@@ -31,4 +41,4 @@ def main(path):
 
 
 if __name__ == '__main__':
-    main(sys.argv[1])
+    main(sys.argv[1], len(sys.argv) > 2 and sys.argv[2] == 'longest')
