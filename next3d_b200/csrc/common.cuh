@@ -39,7 +39,7 @@ struct N3DDeviceState {
     int num_sms;
     unsigned configured;     // bit per kernel, see N3D_CFG_*
 };
-enum { N3D_CFG_CONV = 1u, N3D_CFG_FILL_MOUTH = 2u, N3D_CFG_RENDER16 = 4u, N3D_CFG_RENDER32 = 8u, N3D_CFG_POINTS = 16u, N3D_CFG_FIR_STREAM = 32u };
+enum { N3D_CFG_CONV = 1u, N3D_CFG_FILL_MOUTH = 2u, N3D_CFG_RENDER16 = 4u, N3D_CFG_RENDER32 = 8u, N3D_CFG_POINTS = 16u, N3D_CFG_FIR_STREAM = 32u, N3D_CFG_FIR_DOWN_STREAM = 64u };
 N3DDeviceState* n3d_device_state(void);      // api.cu; nullptr (+ error message) when the current device cannot be queried
 
 // fp32 -> (hi, lo) bf16 pair with hi + lo ~= x to ~16 mantissa bits (used by the 3-product tensor-core scheme).

@@ -459,6 +459,103 @@ __global__ void __launch_bounds__(256) fir_down_split_kernel(const float* __rest
     }
 }
 
+// Streamed form of fir_down_split_kernel (same arithmetic, bit-identical), built like fir_up_stream_kernel: a CTA owns TS sub-pixel rows x
+// TSC sub-pixel columns x all channels of one image ((TSC) * (C / 4) == 256 consumer threads) and a producer thread streams the
+// 2 TS + 3 input rows -- contiguous (2 TSC + 3) * C * 4-byte segments -- through the shared-memory ring with 1-D bulk copies.
+__global__ void __launch_bounds__(kFsThreads, 2) fir_down_stream_kernel(const float* __restrict__ x, int N, int H, int W, int C, int TSC, int TS, int NR,
+                                                                         __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+    using namespace n3d_tc;
+    extern __shared__ __align__(128) uint8_t fs_smem[];
+    const int SH = (H + 2) / 2, SW = (W + 2) / 2, c4n = C >> 2;
+    const int row_f4 = (2 * TSC + 3) * c4n;
+    const uint32_t row_bytes = (uint32_t)row_f4 * 16u;
+    const uint32_t ring = smem_u32(fs_smem), bars = ring + (uint32_t)NR * row_bytes;
+    auto full_bar = [&](int s) { return bars + 8u * (uint32_t)s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (uint32_t)(NR + s); };
+    const int tiles_x = (SW + TSC - 1) / TSC, tiles_y = (SH + TS - 1) / TS;
+    const int bx = blockIdx.x % tiles_x, by = (blockIdx.x / tiles_x) % tiles_y, n = blockIdx.x / (tiles_x * tiles_y);
+    const int SX0 = bx * TSC, SY0 = by * TS, rows_here = min(TS, SH - SY0);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NR; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), kFsConsumers / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int iy_first = 2 * SY0 - 2, iy_last = 2 * (SY0 + rows_here - 1) + 2;
+
+    if (warp == kFsConsumers / 32) {
+        if (lane == 0) {                                        // producer: input columns 2 SX0 - 2 .. 2 SX0 + 2 TSC, clipped to the image
+            const int col_lo = max(2 * SX0 - 2, 0), col_hi = min(2 * SX0 + 2 * TSC, W - 1);
+            const uint32_t bytes = (uint32_t)(col_hi - col_lo + 1) * (uint32_t)C * 4u;
+            const uint32_t dst_off = (uint32_t)(col_lo - (2 * SX0 - 2)) * (uint32_t)C * 4u;
+            const float* src = x + ((int64_t)n * H * W + col_lo) * C;
+            int s = 0; uint32_t ph = 0;
+            for (int iy = iy_first; iy <= iy_last; ++iy) {
+                if (iy < 0 || iy >= H) continue;
+                mbar_wait_short(empty_bar(s), ph ^ 1u);
+                mbar_expect_tx(full_bar(s), bytes);
+                bulk_load_1d(ring + (uint32_t)s * row_bytes + dst_off, src + (int64_t)iy * W * C, bytes, full_bar(s));
+                if (++s == NR) { s = 0; ph ^= 1u; }
+            }
+        }
+        return;
+    }
+
+    const int c4 = threadIdx.x % c4n, j = threadIdx.x / c4n;
+    const int sx = SX0 + j, x0 = 2 * sx;
+    const bool active = sx < SW;                                // the last column tile is ragged (SW = W / 2 + 1)
+    const bool vl = active && x0 >= 2, vm = active && x0 < W, vr = active && x0 + 2 < W;
+    const float4* base = reinterpret_cast<const float4*>(fs_smem) + (2 * j) * c4n + c4;      // input column x0 - 2
+    const float g[4] = {0.125f, 0.375f, 0.375f, 0.125f};
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    int s = 0; uint32_t ph = 0;
+    auto hrow = [&](int iy, float4& h0, float4& h1) {
+        h0 = z; h1 = z;
+        if (iy < 0 || iy >= H) return;
+        mbar_wait_short(full_bar(s), ph);
+        const float4* p = base + s * row_f4;
+        float4 v[5];
+        v[0] = vl ? p[0] : z; v[1] = vl ? p[c4n] : z;
+        v[2] = vm ? p[2 * c4n] : z; v[3] = vm ? p[3 * c4n] : z;
+        v[4] = vr ? p[4 * c4n] : z;
+        h0 = f4_scale(g[0], v[0]); h1 = f4_scale(g[0], v[1]);
+#pragma unroll
+        for (int fx = 1; fx < 4; ++fx) { h0 = f4_fma(g[fx], v[fx], h0); h1 = f4_fma(g[fx], v[fx + 1], h1); }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_bar(s));
+        if (++s == NR) { s = 0; ph ^= 1u; }
+    };
+    const int64_t par_stride = (int64_t)N * SH * SW * C;
+    float4 h[5][2];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) hrow(iy_first + r, h[r][0], h[r][1]);
+    for (int sy = SY0; sy < SY0 + rows_here; ++sy) {
+        const int y0 = sy * 2;
+        hrow(y0 + 1, h[3][0], h[3][1]);
+        hrow(y0 + 2, h[4][0], h[4][1]);
+        if (active) {
+            const int64_t o = (((int64_t)n * SH + sy) * SW + sx) * C + c4 * 4;
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    float4 v = f4_scale(g[0], h[a][b]);
+#pragma unroll
+                    for (int r = 1; r < 4; ++r) v = f4_fma(g[r], h[a + r][b], v);
+                    if (y0 + a > H || x0 + b > W) v = z;        // beyond the (H+1)x(W+1) FIR output: zero pad
+                    uint2 hh, l;
+                    split_bf16x2(v.x, v.y, hh.x, l.x); split_bf16x2(v.z, v.w, hh.y, l.y);
+                    const int64_t off = (int64_t)(a * 2 + b) * par_stride + o;
+                    *reinterpret_cast<uint2*>(hi + off) = hh;
+                    *reinterpret_cast<uint2*>(lo + off) = l;
+                }
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { h[r][0] = h[r + 2][0]; h[r][1] = h[r + 2][1]; }
+    }
+}
+
 // upsample2d: zero-insert x2, pad (2,1), 4x4 FIR * 4.  Polyphase form: out[2i] = .25 x[i-1] + .75 x[i], out[2i+1] = .75 x[i] + .25 x[i+1]
 // per axis.  thread = (input pixel (i,j), VEC channels) -> the 2x2 output block from the 3x3 input neighbourhood.
 template <int VEC>
@@ -662,6 +759,31 @@ extern "C" int n3d_splitk_epilogue(const float* partial, int S, int64_t split_st
 extern "C" int n3d_fir_down_split(const float* x, int N, int H, int W, int C, void* hi, void* lo, void* stream) {
     N3D_CHECK_ARG(x && hi && lo, "n3d_fir_down_split: null pointer");
     N3D_CHECK_ARG(C % 4 == 0 && H % 2 == 0 && W % 2 == 0, "n3d_fir_down_split: C %% 4 and even H, W required");
+    {   // streamed variant for the large layers (see fir_down_stream_kernel); N3D_FIR_STREAM=0: the register-tiled kernel
+        const char* e = getenv("N3D_FIR_STREAM");
+        const int c4n = C / 4, SH = (H + 2) / 2, SW = (W + 2) / 2;
+        const int TSC = (c4n >= 8 && c4n <= 128 && 256 % c4n == 0) ? 256 / c4n : 0;
+        int TS = 0;
+        for (int ts = 32; ts >= 16 && TSC; ts >>= 1)
+            if ((int64_t)N * n3d_div_up(SW, TSC) * n3d_div_up(SH, ts) >= 148) { TS = ts; break; }
+        if ((!e || atoi(e) != 0) && TS > 0 && ((uintptr_t)x & 15) == 0) {
+            const int row_bytes = (2 * TSC + 3) * C * 4, NR = 4;
+            const int smem = NR * row_bytes + 16 * NR;
+            N3DDeviceState* D = n3d_device_state();
+            if (!D) return N3D_ERR_CUDA;
+            if (!(D->configured & N3D_CFG_FIR_DOWN_STREAM)) {
+                if (cudaFuncSetAttribute(fir_down_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024) != cudaSuccess) {
+                    n3d_set_error("n3d_fir_down_split: cannot raise dynamic shared memory to 112 KiB");
+                    return N3D_ERR_CUDA;
+                }
+                D->configured |= N3D_CFG_FIR_DOWN_STREAM;
+            }
+            fir_down_stream_kernel<<<N * n3d_div_up(SW, TSC) * n3d_div_up(SH, TS), kFsThreads, smem, (cudaStream_t)stream>>>(
+                x, N, H, W, C, TSC, TS, NR, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+            N3D_CHECK_LAUNCH("n3d_fir_down_split");
+            return N3D_OK;
+        }
+    }
     const int S = fir_strip_rows((int64_t)N * ((W + 2) / 2) * (C / 4), (H + 2) / 2);
     const int64_t total = (int64_t)N * n3d_div_up((H + 2) / 2, S) * ((W + 2) / 2) * (C / 4);
     fir_down_split_kernel<<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(x, N, H, W, C, S, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);

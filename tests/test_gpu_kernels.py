@@ -268,6 +268,35 @@ def test_downconv(K, N, Cin, Cout, res):
     assert range_rel_err(out.permute(0, 3, 1, 2).cpu(), ref) < 3e-5
 
 
+@pytest.mark.parametrize('N,C,H', [(3, 128, 256), (4, 256, 128), (8, 512, 64), (8, 64, 128), (2, 128, 250)])
+def test_fir_down_streamed_kernel_is_bit_identical(K, N, C, H, monkeypatch):
+    """Encoder stride-2 path: the streamed FIR-down kernel (large layers) == the register-tiled one bit for bit (four parity images,
+    ragged last row / column tiles, zero padding), and both == an fp64 evaluation of upfirdn2d(pad 2) split by output parity."""
+    g = _g(41 + C + H)
+    x = torch.randn(N, H, H, C, generator=g).to(DEV)
+    SH = (H + 2) // 2
+
+    def run(mode):
+        monkeypatch.setenv('N3D_FIR_STREAM', mode)
+        hi = torch.full((4 * N, SH, SH, C), 7.0, device=DEV, dtype=torch.bfloat16)
+        lo = torch.full_like(hi, 7.0)
+        K.fir_down_split(x, hi, lo)
+        torch.cuda.synchronize()
+        return hi, lo
+
+    (h1, l1), (h0, l0) = run('1'), run('0')
+    assert torch.equal(h1, h0) and torch.equal(l1, l0)
+    f1 = torch.tensor([1., 3., 3., 1.], dtype=torch.float64, device=DEV) / 8
+    xx = F.pad(x.double().permute(0, 3, 1, 2), (2, 2, 2, 2))
+    fo = F.conv2d(xx.reshape(N * C, 1, H + 4, H + 4), torch.outer(f1, f1)[None, None]).reshape(N, C, H + 1, H + 1)
+    fo = F.pad(fo, (0, 1, 0, 1))                                  # (H+2) x (H+2): the extra row / column is the zero pad
+    got = _join(h1, l1).reshape(4, N, SH, SH, C)
+    for a in (0, 1):
+        for b in (0, 1):
+            ref = fo[:, :, a::2, b::2].permute(0, 2, 3, 1)
+            assert range_rel_err(got[a * 2 + b].cpu(), ref.cpu()) < 2e-5, (a, b)
+
+
 # ------------------------------------------------------------------------------------------------ glue kernels
 def test_styles_demod(K):
     g = _g(23)
