@@ -70,10 +70,11 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-// Short suspended wait (20 us hint per try), bounded to about a second: for kernels whose stages complete within microseconds.
+// Suspended wait with a short hint (20 us per try) for kernels whose stages complete within microseconds; bounded (a protocol bug
+// traps after about a minute instead of hanging; generous enough for profiler replays and time-sliced contexts).
 __device__ __forceinline__ void mbar_wait_short(uint32_t bar, uint32_t parity) {
 #pragma unroll 1
-    for (uint32_t it = 0; it < (1u << 16); ++it) {
+    for (uint32_t it = 0; it < (1u << 22); ++it) {
         uint32_t ok;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
