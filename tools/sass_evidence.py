@@ -4,7 +4,7 @@ import collections
 import re
 import subprocess
 
-PAT = re.compile(r'^(UTCHMMA|UTMALDG|LDTM|UTCBAR|UTCATOMSWS|SYNCS|STG\.E\.ENL2\.256|LDG\.E\.ENL2\.256|FFMA2|FMUL2|FADD2|F2FP\.BF16)')
+PAT = re.compile(r'^(UTCHMMA|UTMALDG|UBLKCP|LDTM|UTCBAR|UTCATOMSWS|SYNCS|STG\.E\.ENL2\.256|LDG\.E\.ENL2\.256|FFMA2|FMUL2|FADD2|F2FP\.BF16)')
 out = subprocess.run(['cuobjdump', '-sass', 'next3d_b200/libnext3d_b200.so'], capture_output=True, text=True).stdout
 cur, cnt = None, collections.Counter()
 for l in out.splitlines():
@@ -16,7 +16,7 @@ for l in out.splitlines():
     if m and cur and PAT.match(m.group(1)):
         cnt[(cur, m.group(1))] += 1
 print('# cuobjdump -sass next3d_b200/libnext3d_b200.so : count of Blackwell-specific SASS mnemonics per kernel')
-print('# (UTCHMMA = tcgen05.mma, UTMALDG = TMA cp.async.bulk.tensor, LDTM = tcgen05.ld, UTCBAR = tcgen05.commit, UTCATOMSWS = tcgen05.alloc/dealloc,')
+print('# (UTCHMMA = tcgen05.mma, UTMALDG = TMA cp.async.bulk.tensor, UBLKCP = 1-D cp.async.bulk, LDTM = tcgen05.ld, UTCBAR = tcgen05.commit, UTCATOMSWS = tcgen05.alloc/dealloc,')
 print('#  SYNCS = mbarrier, STG/LDG.E.ENL2.256 = 256-bit global accesses, FFMA2/FMUL2/FADD2 = packed fp32x2, F2FP.BF16 = packed bf16 convert)')
 for (k, op), n in sorted(cnt.items()):
     print(f'{n:5d} {k[:70]:70s} {op}')
