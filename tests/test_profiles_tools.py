@@ -31,3 +31,21 @@ def test_dram_table_and_bench_lookup(tmp_path):
     tr, src = bench._traffic('conv_gemm_kernel')
     assert tr == ref['conv_gemm_kernel']['dram_bytes_per_launch'] and 'r02_dram_traffic.json' in src
     assert bench._traffic('no_such_kernel') == (None, None)
+
+
+def test_every_launched_kernel_has_a_committed_ncu_summary():
+    """north_star: every kernel evidenced by a committed ncu capture.  Every kernel of the launch list of one forward appears in an
+    `ncu --set full` summary under profiles/; the one kernel added after the last full capture is evidenced by the launch list itself
+    (time + DRAM bytes per launch) and must then appear in the DRAM table."""
+    import glob
+    names = [l.split()[0] for l in open(os.path.join(ROOT, 'profiles', 'r02_launches_summary.txt')) if len(l.split()) == 4 and l.split()[1].isdigit()]
+    assert len(names) >= 20
+    full = ''.join(open(f).read() for f in glob.glob(os.path.join(ROOT, 'profiles', 'r02_ncu_*.txt')))
+    dram = json.load(open(os.path.join(ROOT, 'profiles', 'r02_dram_traffic.json')))['kernels']
+    launch_list_only = {'fir_down_stream_kernel'}
+    for n in names:
+        base = n.split('<')[0]
+        if base in launch_list_only:
+            assert base in dram and dram[base]['dram_bytes_per_launch'] > 0
+        else:
+            assert base in full, f'no ncu --set full summary for {n}'
